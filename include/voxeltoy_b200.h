@@ -1,0 +1,170 @@
+/*
+ * voxeltoy_b200.h -- C ABI of the B200-native voxelToy hot path.
+ *
+ * This is the device boundary of the reference: every entry point below replaces a
+ * group of OpenGL calls the reference's C++ classes (src/renderer, src/voxelize,
+ * src/renderer/services) issue directly. The reference has no FFI of its own; the
+ * file:line after each declaration names the GL call site it replaces
+ * (paths relative to /root/reference/src).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no C++/torch types cross the boundary.
+ *  - every function returns 0 (VT_OK) or a negative vt_status; the message of the
+ *    last failure on a context is vt_last_error(ctx).
+ *  - host pointers are borrowed for the duration of the call and copied.
+ *  - device memory is owned by the context; one context per GPU; a context is
+ *    externally synchronised (one host thread at a time -- the reference's single
+ *    GL thread).
+ *  - work is enqueued on the context's CUDA stream; only vt_read_* / vt_sync /
+ *    vt_get_* block.
+ *  - matrices are row-major float[16] in the column-vector convention, exactly the
+ *    arrays the reference hands to glUniformMatrix4fv(..., GL_TRUE, &m.x[0][0]).
+ *  - images are W*H RGBA float32, row 0 = BOTTOM row (GL window origin); the host
+ *    Renderer::saveImage flips (renderer/renderer.cpp:1132-1136).
+ *  - there is NO CPU fallback: without a CUDA device vt_create fails.
+ */
+#ifndef VOXELTOY_B200_H
+#define VOXELTOY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vt_ctx vt_ctx;
+
+typedef enum vt_status {
+    VT_OK = 0,
+    VT_ERR_INVALID = -1,      /* bad argument / call order                      */
+    VT_ERR_CUDA = -2,         /* a CUDA runtime call failed (see vt_last_error) */
+    VT_ERR_NO_DEVICE = -3,    /* no usable CUDA device: there is no CPU path    */
+    VT_ERR_STATE = -4         /* scene / frame not set up yet                   */
+} vt_status;
+
+/* cameraLensModel, camera/cameraParameters.h:23-28 */
+enum { VT_LENS_PINHOLE = 0, VT_LENS_THIN = 1, VT_LENS_ORTHO = 2 };
+/* Renderer::Integrator, renderer/renderer.h:113-118 */
+enum { VT_INTEGRATOR_PATHTRACER = 0, VT_INTEGRATOR_EDIT_MODE = 1 };
+/* work partition of one frame across `world` contexts */
+enum { VT_PART_NONE = 0, VT_PART_TILES = 1, VT_PART_SAMPLES = 2 };
+
+/* uniforms uploaded by Renderer::updateCamera, renderer/renderer.cpp:410-444 */
+typedef struct vt_camera {
+    float inv_modelview[16];   /* cameraInverseModelView  :420-423 */
+    float proj[16];            /* cameraProj              :425-428 */
+    float inv_proj[16];        /* cameraInverseProj       :430-433 */
+    float near_z, far_z;       /* cameraNear / cameraFar  :417-418 (near feeds the pick ray, selectVoxel.vs:41) */
+    float lens_radius;         /* cameraLensRadius        :439 */
+    int32_t lens_model;        /* cameraLensModel         :440 */
+} vt_camera;
+
+/* uniforms uploaded by Renderer::updateRenderSettings, renderer/renderer.cpp:1071-1101,
+ * plus the frame size of resizeFrame (:448-554) and the integrator switch (:676-680) */
+typedef struct vt_settings {
+    int32_t width, height;             /* viewport = (0,0,width,height) :468-472 */
+    int32_t max_bounces;               /* pathtracerMaxNumBounces */
+    int32_t integrator;                /* VT_INTEGRATOR_* */
+    float bg_top[3], bg_bottom[3];     /* backgroundColorTop / Bottom */
+    int32_t use_env_image;             /* backgroundUseImage */
+    float env_rotation_rad;            /* backgroundRotationRadians */
+    float wireframe_opacity, wireframe_thickness;
+} vt_settings;
+
+/* algorithmic work counters: bytes_per_sample = 4S + 16R + 36H + 4E + 64Q + 32 */
+typedef struct vt_counters {
+    uint64_t dda_steps;     /* S: DDA iterations that fetched a voxel */
+    uint64_t rand_calls;    /* R */
+    uint64_t material_evals;/* H */
+    uint64_t cdf_loads;     /* E */
+    uint64_t env_lookups;   /* Q */
+    uint64_t paths;         /* samples (pixel-passes) */
+    uint64_t kernel_launches; /* launches of this library's kernels since vt_create */
+} vt_counters;
+
+typedef void (*vt_log_fn)(const char* msg, void* user);   /* log/logger.h:7-11 */
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int vt_create(int device, vt_ctx** out);               /* Renderer::initialize, renderer.cpp:76-147 (glewInit + resource creation) */
+void vt_destroy(vt_ctx* ctx);
+const char* vt_last_error(const vt_ctx* ctx);          /* Renderer::getStatus, renderer.h:95 */
+int vt_set_logger(vt_ctx* ctx, vt_log_fn fn, void* user); /* Renderer::setLogger, renderer.cpp:72-75 */
+int vt_set_stream(vt_ctx* ctx, void* cuda_stream);     /* interop: run on a caller-owned cudaStream_t (NULL = the context's own) */
+int vt_sync(vt_ctx* ctx);                              /* glFinish */
+
+/* ---- scene upload: Renderer::createVoxelDataTexture, renderer.cpp:833-940 -------- */
+/* R32I material-offset grid, x fastest, -1 = empty (glTexImage3D :863-872). NULL = all empty.
+ * Derives world bounds / voxel size (:845-850) and the bit-packed occupancy + its mip. */
+int vt_volume_upload(vt_ctx* ctx, const int32_t* mat_offsets, int X, int Y, int Z);
+int vt_materials_upload(vt_ctx* ctx, const float* data, size_t n_floats);            /* glTexImage1D :879-887 */
+int vt_material_update(vt_ctx* ctx, uint32_t offset, const float* values, int n);    /* updateMaterialColor/Value, renderer.cpp:1205-1235 */
+int vt_emissive_upload(vt_ctx* ctx, const int32_t* voxel_indices, size_t n);         /* glTexImage1D :894-902 */
+int vt_read_volume(vt_ctx* ctx, int32_t* mat_offsets_out);                           /* glGetTexImage of the offset texture */
+int vt_read_materials(vt_ctx* ctx, float* out, size_t n_floats);                     /* getMaterials, renderer.cpp:1142-1160 */
+int vt_get_volume_info(vt_ctx* ctx, int32_t res[3], float bounds_min[3], float bounds_max[3], float voxel_size[3]);
+
+/* noise texture, renderer.cpp:740-760. rgba == NULL: the reference's own table (first w*h*4 outputs
+ * of glibc rand()/RAND_MAX with the default seed), generated inside the library. */
+int vt_noise_upload(vt_ctx* ctx, const float* rgba, int w, int h);
+
+/* environment map + CDFs: Renderer::loadBackgroundImage, renderer.cpp:983-1046 */
+int vt_env_upload(vt_ctx* ctx, const float* rgb, int w, int h,
+                  const float* cdf_u, int cdf_u_w, int cdf_u_h,
+                  const float* cdf_v, int cdf_v_n, float integral);
+int vt_env_clear(vt_ctx* ctx);
+
+/* ---- per-frame state -------------------------------------------------------------- */
+int vt_set_camera(vt_ctx* ctx, const vt_camera* cam);       /* updateCamera, renderer.cpp:410-444 */
+int vt_set_settings(vt_ctx* ctx, const vt_settings* st);    /* updateRenderSettings :1057-1106, resizeFrame :448-554 */
+int vt_set_focal_distance(vt_ctx* ctx, float d);            /* FocalDistanceData SSBO, renderer.cpp:712-720 */
+int vt_get_focal_distance(vt_ctx* ctx, float* d);
+int vt_set_selection(vt_ctx* ctx, const int32_t index[4], const float normal[4]);  /* SelectVoxelData SSBO, renderer.cpp:723-737 */
+int vt_get_selection(vt_ctx* ctx, int32_t index[4], float normal[4]);
+
+/* ---- the hot path: one or more progressive passes ------------------------------------ */
+int vt_reset_accumulation(vt_ctx* ctx);                     /* resetRender, renderer.cpp:941-945 */
+/* K1+K2 fused: passes first_sample .. first_sample+n_passes-1 of the current integrator, each folded into
+ * the running average with n = number of passes accumulated so far (renderer.cpp:594-611, accumulation.fs:10-18).
+ * first_sample is the `sampleCount` uniform of the first pass. */
+int vt_render(vt_ctx* ctx, int first_sample, int n_passes);
+int vt_get_num_samples(vt_ctx* ctx, int* n);                /* m_numberSamples */
+int vt_read_average(vt_ctx* ctx, float* rgba_out);          /* glGetTexImage(average), renderer.cpp:1119-1127 */
+int vt_read_primary_hits(vt_ctx* ctx, int32_t* out);        /* per pixel: linear voxel index, -1 miss, -2 ground (last pass) */
+int vt_enable_primary_hits(vt_ctx* ctx, int enable);
+/* multi-GPU: restrict this context to its share of the frame (tiles) or of the samples. */
+int vt_set_partition(vt_ctx* ctx, int mode, int rank, int world);
+/* sample-partition mode keeps a running SUM instead of an average; expose the device buffer so the caller's
+ * collective (NCCL through torch.distributed) can reduce it in place. W*H float4. */
+void* vt_accum_device_ptr(vt_ctx* ctx);
+int vt_counters_enable(vt_ctx* ctx, int enable);
+int vt_get_counters(vt_ctx* ctx, vt_counters* out);
+int vt_reset_counters(vt_ctx* ctx);
+
+/* ---- voxelizer: GPUVoxelizer::voxelizeMesh, voxelize/gpuVoxelizer.cpp:46-72 (+ Mesh::draw, mesh/mesh.cpp:55-59) ----
+ * Clears the grid to `empty`, then writes fill_offset into every voxel the THIN surface voxelization
+ * touches (voxelize.gs:118-251). Replaces the volume of the context (resolution X,Y,Z). */
+int vt_voxelize(vt_ctx* ctx, const float* xyz, size_t n_verts, const uint32_t* indices, size_t n_indices,
+                const float model_transform[16], int X, int Y, int Z, int32_t fill_offset);
+/* replace material offsets of solid voxels by rule(x,y,z): new-build extension used by BASELINE config 3. */
+int vt_volume_assign_materials(vt_ctx* ctx, const int32_t* offsets_table, int n_table, int rule);
+/* elapsed GPU milliseconds of the last vt_voxelize (clear + scatter + derive), cudaEvent-timed */
+int vt_get_last_voxelize_ms(vt_ctx* ctx, float* ms);
+
+/* ---- services: renderer/services/*.cpp (1-vertex "compute" draws, service.cpp:10-20) ---- */
+int vt_pick(vt_ctx* ctx, float px, float py);                /* RendererServiceSelectActiveVoxel -> selectVoxel.vs */
+int vt_pick_focal(vt_ctx* ctx, float px, float py);          /* RendererServiceSetFocalDistance  -> focalDistance.vs */
+int vt_add_voxel(vt_ctx* ctx, float motion_x, float motion_y); /* RendererServiceAddVoxel -> addVoxel.vs (motion already y-flipped, serviceAddVoxel.cpp:74) */
+int vt_remove_voxel(vt_ctx* ctx);                            /* RendererServiceRemoveVoxel -> removeVoxel.vs */
+
+/* ---- diagnostics -------------------------------------------------------------------- */
+int vt_device_count(void);
+const char* vt_version(void);
+/* test hook: trace n rays (origin xyz, dir xyz interleaved, 6 floats each) through the current volume with
+ * the DDA of dda.h:63-100; out_hit[4n] = (x,y,z, code) with code 1 voxel hit, 2 ground, 0 miss. */
+int vt_debug_trace_rays(vt_ctx* ctx, const float* rays, size_t n, float* out_hit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXELTOY_B200_H */

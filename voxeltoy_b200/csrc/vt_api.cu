@@ -1,0 +1,638 @@
+// vt_api.cu -- implementation of the C ABI declared in include/voxeltoy_b200.h.
+// Host side of the device boundary: owns device memory, the stream, and launches the
+// kernels of vt_kernels.cuh. No OpenGL, no CPU fallback: every compute entry point
+// needs a live CUDA context and fails with VT_ERR_CUDA / VT_ERR_NO_DEVICE otherwise.
+#include "../../include/voxeltoy_b200.h"
+#include "vt_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace vt;
+
+struct vt_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    vt_log_fn log_fn = nullptr;
+    void* log_user = nullptr;
+
+    // volume
+    int X = 0, Y = 0, Z = 0, BX = 0, BY = 0, BZ = 0, SX = 0, SY = 0, SZ = 0;
+    int32_t* d_mat = nullptr;
+    unsigned long long* d_bricks = nullptr;
+    unsigned long long* d_supers = nullptr;
+    float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0}, vsize[3] = {0, 0, 0};
+    // scene arrays
+    float* d_materials = nullptr; size_t n_materials = 0;
+    int32_t* d_emissive = nullptr; size_t n_emissive = 0;
+    float4* d_noise = nullptr; int noise_w = 0, noise_h = 0;
+    float4* d_env = nullptr; int env_w = 0, env_h = 0;
+    float* d_cdf_u = nullptr; int cdf_u_w = 0, cdf_u_h = 0;
+    float* d_cdf_v = nullptr; int cdf_v_n = 0;
+    float env_integral = 0.f;
+    // frame
+    vt_camera cam{};
+    vt_settings st{};
+    bool have_cam = false, have_settings = false;
+    float4* d_accum = nullptr; size_t accum_pixels = 0;
+    int32_t* d_primary = nullptr; bool primary_enabled = false;
+    int num_samples = 0;
+    Shared* d_shared = nullptr;
+    int* d_result = nullptr;
+    // partition
+    int part_mode = VT_PART_NONE, part_rank = 0, part_world = 1;
+    // counters
+    Counters* d_counters = nullptr; bool count_enabled = false;
+    uint64_t paths = 0, launches = 0;
+    // voxelizer timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr; float last_voxelize_ms = 0.f;
+};
+
+static int fail(vt_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) { c->err = buf; if (c->log_fn) c->log_fn(buf, c->log_user); }
+    return code;
+}
+#define VT_CUDA(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail((c), VT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define VT_REQ(c, cond, msg) do { if (!(cond)) return fail((c), VT_ERR_INVALID, "%s", (msg)); } while (0)
+#define VT_BIND(c) VT_CUDA(c, cudaSetDevice((c)->device))
+
+static int grid_for(size_t n, int block) { size_t g = (n + block - 1) / block; const size_t cap = 148 * 32; return (int)(g < 1 ? 1 : (g > cap ? cap : g)); }
+
+extern "C" {
+
+int vt_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+const char* vt_version(void) { return "voxeltoy_b200 0.1 (sm_100a)"; }
+
+// glibc rand() (TYPE_3 additive feedback, default seed 1), renderer/renderer.cpp:741-744
+static void default_noise(std::vector<float>& out, size_t n)
+{
+    std::vector<uint32_t> r(n + 344);
+    int32_t s[34];
+    s[0] = 1;
+    for (int i = 1; i < 31; ++i) {
+        const int64_t hi = s[i - 1] / 127773, lo = s[i - 1] % 127773;
+        int64_t w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        s[i] = (int32_t)w;
+    }
+    for (int i = 0; i < 31; ++i) r[i] = (uint32_t)s[i];
+    for (int i = 31; i < 34; ++i) r[i] = r[i - 31];
+    for (size_t i = 34; i < 344; ++i) r[i] = r[i - 31] + r[i - 3];
+    out.resize(n);
+    for (size_t i = 344; i < 344 + n; ++i) {
+        r[i] = r[i - 31] + r[i - 3];
+        out[i - 344] = (float)(int32_t)(r[i] >> 1) / (float)2147483647;   // (float)rand() / RAND_MAX
+    }
+}
+
+int vt_create(int device, vt_ctx** out)
+{
+    if (!out) return VT_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return VT_ERR_NO_DEVICE;
+    vt_ctx* c = new vt_ctx();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c; return VT_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    Shared sh;
+    sh.focal_distance = 99999999.0f;                                  // renderer.cpp:712-720
+    sh.sel_index[0] = sh.sel_index[1] = sh.sel_index[2] = sh.sel_index[3] = 0;   // :723-737
+    sh.sel_normal[0] = 1.f; sh.sel_normal[1] = sh.sel_normal[2] = sh.sel_normal[3] = 0.f;
+    if (cudaMalloc(&c->d_shared, sizeof(Shared)) != cudaSuccess || cudaMalloc(&c->d_result, 4 * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&c->d_counters, sizeof(Counters)) != cudaSuccess ||
+        cudaMemcpy(c->d_shared, &sh, sizeof sh, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(c->d_counters, 0, sizeof(Counters)) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        vt_destroy(c); return VT_ERR_CUDA;
+    }
+    // defaults of the Renderer constructor (renderer.cpp:41-65) + pathTracer.fs:25-26,40-41
+    c->st.width = 512; c->st.height = 512; c->st.max_bounces = 1; c->st.integrator = VT_INTEGRATOR_PATHTRACER;
+    c->st.bg_top[0] = 153.0f / 255 * 2; c->st.bg_top[1] = 187.0f / 255 * 2; c->st.bg_top[2] = 201.0f / 255 * 2;
+    c->st.bg_bottom[0] = 77.0f / 255; c->st.bg_bottom[1] = 64.0f / 255; c->st.bg_bottom[2] = 50.0f / 255;
+    c->st.wireframe_opacity = 0.f; c->st.wireframe_thickness = 0.01f;
+    *out = c;
+    // noise texture + 16^3 empty volume, as Renderer::initialize does (renderer.cpp:94-98)
+    int rc = vt_noise_upload(c, nullptr, 1024, 1024);
+    if (rc == VT_OK) rc = vt_volume_upload(c, nullptr, 16, 16, 16);
+    if (rc != VT_OK) { vt_destroy(c); *out = nullptr; return rc; }
+    return VT_OK;
+}
+
+void vt_destroy(vt_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_mat); cudaFree(c->d_bricks); cudaFree(c->d_supers); cudaFree(c->d_materials); cudaFree(c->d_emissive);
+    cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum);
+    cudaFree(c->d_primary); cudaFree(c->d_shared); cudaFree(c->d_result); cudaFree(c->d_counters);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* vt_last_error(const vt_ctx* c) { return c ? c->err.c_str() : "null context"; }
+int vt_set_logger(vt_ctx* c, vt_log_fn fn, void* user) { if (!c) return VT_ERR_INVALID; c->log_fn = fn; c->log_user = user; return VT_OK; }
+int vt_set_stream(vt_ctx* c, void* s) { if (!c) return VT_ERR_INVALID; c->stream = s ? (cudaStream_t)s : c->own_stream; return VT_OK; }
+int vt_sync(vt_ctx* c) { if (!c) return VT_ERR_INVALID; VT_BIND(c); VT_CUDA(c, cudaStreamSynchronize(c->stream)); return VT_OK; }
+
+// ---- volume ------------------------------------------------------------------------------------
+static void volume_bounds(vt_ctx* c)
+{
+    // renderer.cpp:845-850 and :926-929
+    const int m = std::max(c->X, std::max(c->Y, c->Z));
+    const float voxel = 1000.0f / (float)m;
+    const int r[3] = { c->X, c->Y, c->Z };
+    for (int i = 0; i < 3; ++i) {
+        const float sz = voxel * (float)r[i];
+        c->bmin[i] = -sz * 0.5f; c->bmax[i] = sz * 0.5f;
+        c->vsize[i] = (c->bmax[i] - c->bmin[i]) / (float)r[i];
+    }
+}
+
+static int alloc_volume(vt_ctx* c, int X, int Y, int Z)
+{
+    VT_REQ(c, X > 0 && Y > 0 && Z > 0 && X <= 2048 && Y <= 2048 && Z <= 2048, "volume resolution must be in [1, 2048]^3");
+    if (X != c->X || Y != c->Y || Z != c->Z || !c->d_mat) {
+        cudaFree(c->d_mat); cudaFree(c->d_bricks); cudaFree(c->d_supers);
+        c->d_mat = nullptr; c->d_bricks = nullptr; c->d_supers = nullptr;
+        c->X = X; c->Y = Y; c->Z = Z;
+        c->BX = (X + 3) / 4; c->BY = (Y + 3) / 4; c->BZ = (Z + 3) / 4;
+        c->SX = (c->BX + 3) / 4; c->SY = (c->BY + 3) / 4; c->SZ = (c->BZ + 3) / 4;
+        VT_CUDA(c, cudaMalloc(&c->d_mat, sizeof(int32_t) * (size_t)X * Y * Z));
+        VT_CUDA(c, cudaMalloc(&c->d_bricks, sizeof(unsigned long long) * (size_t)c->BX * c->BY * c->BZ));
+        VT_CUDA(c, cudaMalloc(&c->d_supers, sizeof(unsigned long long) * (size_t)c->SX * c->SY * c->SZ));
+    }
+    volume_bounds(c);
+    return VT_OK;
+}
+
+static int rebuild_occupancy(vt_ctx* c)
+{
+    const size_t nb = (size_t)c->BX * c->BY * c->BZ, ns = (size_t)c->SX * c->SY * c->SZ;
+    VT_CUDA(c, cudaMemsetAsync(c->d_bricks, 0, nb * 8, c->stream));
+    VT_CUDA(c, cudaMemsetAsync(c->d_supers, 0, ns * 8, c->stream));
+    const size_t rows = (size_t)c->BX * c->Y * c->Z;
+    vt_build_bricks_kernel<<<grid_for(rows, 256), 256, 0, c->stream>>>(c->d_mat, c->d_bricks, c->X, c->Y, c->Z, c->BX, c->BX * c->BY);
+    vt_build_supers_kernel<<<grid_for(nb, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_supers, c->BX, c->BY, c->BZ, c->SX, c->SX * c->SY);
+    c->launches += 2;
+    VT_CUDA(c, cudaGetLastError());
+    return VT_OK;
+}
+
+int vt_volume_upload(vt_ctx* c, const int32_t* mat, int X, int Y, int Z)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_BIND(c);
+    int rc = alloc_volume(c, X, Y, Z);
+    if (rc != VT_OK) return rc;
+    const size_t n = (size_t)X * Y * Z;
+    if (mat) VT_CUDA(c, cudaMemcpyAsync(c->d_mat, mat, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    else VT_CUDA(c, cudaMemsetAsync(c->d_mat, 0xff, n * sizeof(int32_t), c->stream));
+    rc = rebuild_occupancy(c);
+    if (rc != VT_OK) return rc;
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VT_OK;
+}
+
+static int upload_array(vt_ctx* c, void** dptr, const void* src, size_t bytes)
+{
+    cudaFree(*dptr); *dptr = nullptr;
+    if (bytes == 0) return VT_OK;
+    VT_CUDA(c, cudaMalloc(dptr, bytes));
+    VT_CUDA(c, cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+    return VT_OK;
+}
+
+int vt_materials_upload(vt_ctx* c, const float* data, size_t n)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, data || n == 0, "null material data");
+    VT_BIND(c);
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_materials = n;
+    return upload_array(c, (void**)&c->d_materials, data, n * sizeof(float));
+}
+
+int vt_material_update(vt_ctx* c, uint32_t offset, const float* v, int n)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, v && n > 0 && (size_t)offset + (size_t)n <= c->n_materials, "material update out of range");
+    VT_BIND(c);
+    VT_CUDA(c, cudaMemcpyAsync(c->d_materials + offset, v, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VT_OK;
+}
+
+int vt_emissive_upload(vt_ctx* c, const int32_t* idx, size_t n)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, idx || n == 0, "null emissive list");
+    VT_BIND(c);
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_emissive = n;
+    return upload_array(c, (void**)&c->d_emissive, idx, n * sizeof(int32_t));
+}
+
+int vt_read_volume(vt_ctx* c, int32_t* out)
+{
+    if (!c || !out) return VT_ERR_INVALID;
+    VT_BIND(c);
+    VT_CUDA(c, cudaMemcpyAsync(out, c->d_mat, sizeof(int32_t) * (size_t)c->X * c->Y * c->Z, cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VT_OK;
+}
+
+int vt_read_materials(vt_ctx* c, float* out, size_t n)
+{
+    if (!c || !out) return VT_ERR_INVALID;
+    VT_REQ(c, n <= c->n_materials, "read past the material array");
+    VT_BIND(c);
+    VT_CUDA(c, cudaMemcpyAsync(out, c->d_materials, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VT_OK;
+}
+
+int vt_get_volume_info(vt_ctx* c, int32_t res[3], float bmin[3], float bmax[3], float vs[3])
+{
+    if (!c) return VT_ERR_INVALID;
+    if (res) { res[0] = c->X; res[1] = c->Y; res[2] = c->Z; }
+    for (int i = 0; i < 3; ++i) { if (bmin) bmin[i] = c->bmin[i]; if (bmax) bmax[i] = c->bmax[i]; if (vs) vs[i] = c->vsize[i]; }
+    return VT_OK;
+}
+
+int vt_noise_upload(vt_ctx* c, const float* rgba, int w, int h)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, w > 0 && h > 0, "bad noise size");
+    VT_BIND(c);
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<float> gen;
+    if (!rgba) { default_noise(gen, (size_t)w * h * 4); rgba = gen.data(); }
+    c->noise_w = w; c->noise_h = h;
+    return upload_array(c, (void**)&c->d_noise, rgba, sizeof(float) * 4 * (size_t)w * h);
+}
+
+int vt_env_upload(vt_ctx* c, const float* rgb, int w, int h, const float* cdf_u, int cuw, int cuh,
+                  const float* cdf_v, int cvn, float integral)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, rgb && cdf_u && cdf_v && w > 0 && h > 0 && cuw > 1 && cuh > 0 && cvn > 1, "bad environment arrays");
+    VT_BIND(c);
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<float> rgba((size_t)w * h * 4);
+    for (size_t i = 0; i < (size_t)w * h; ++i) {                        // GL_RGB -> GL_RGBA32F, alpha 1 (renderer.cpp:994-1002)
+        rgba[4 * i] = rgb[3 * i]; rgba[4 * i + 1] = rgb[3 * i + 1]; rgba[4 * i + 2] = rgb[3 * i + 2]; rgba[4 * i + 3] = 1.0f;
+    }
+    int rc = upload_array(c, (void**)&c->d_env, rgba.data(), rgba.size() * sizeof(float));
+    if (rc == VT_OK) rc = upload_array(c, (void**)&c->d_cdf_u, cdf_u, sizeof(float) * (size_t)cuw * cuh);
+    if (rc == VT_OK) rc = upload_array(c, (void**)&c->d_cdf_v, cdf_v, sizeof(float) * (size_t)cvn);
+    if (rc != VT_OK) return rc;
+    c->env_w = w; c->env_h = h; c->cdf_u_w = cuw; c->cdf_u_h = cuh; c->cdf_v_n = cvn; c->env_integral = integral;
+    return VT_OK;
+}
+
+int vt_env_clear(vt_ctx* c)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_BIND(c);
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v);
+    c->d_env = nullptr; c->d_cdf_u = nullptr; c->d_cdf_v = nullptr;
+    c->env_w = c->env_h = c->cdf_u_w = c->cdf_u_h = c->cdf_v_n = 0; c->env_integral = 0.f;
+    return VT_OK;
+}
+
+// ---- per-frame state ----------------------------------------------------------------------------
+int vt_set_camera(vt_ctx* c, const vt_camera* cam) { if (!c || !cam) return VT_ERR_INVALID; c->cam = *cam; c->have_cam = true; return VT_OK; }
+
+int vt_set_settings(vt_ctx* c, const vt_settings* st)
+{
+    if (!c || !st) return VT_ERR_INVALID;
+    VT_REQ(c, st->width > 0 && st->height > 0 && st->width <= 16384 && st->height <= 16384, "bad frame size");
+    VT_REQ(c, st->max_bounces >= 0, "negative bounce count");
+    VT_BIND(c);
+    const size_t px = (size_t)st->width * st->height;
+    if (px != c->accum_pixels || st->width != c->st.width || !c->d_accum) {
+        VT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_accum); cudaFree(c->d_primary); c->d_accum = nullptr; c->d_primary = nullptr;
+        VT_CUDA(c, cudaMalloc(&c->d_accum, px * sizeof(float4)));
+        VT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, px * sizeof(float4), c->stream));
+        c->accum_pixels = px;
+        c->num_samples = 0;
+    }
+    c->st = *st;
+    c->have_settings = true;
+    return VT_OK;
+}
+
+static int shared_rw(vt_ctx* c, Shared* host, bool write)
+{
+    VT_BIND(c);
+    if (write) VT_CUDA(c, cudaMemcpyAsync(c->d_shared, host, sizeof(Shared), cudaMemcpyHostToDevice, c->stream));
+    else VT_CUDA(c, cudaMemcpyAsync(host, c->d_shared, sizeof(Shared), cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VT_OK;
+}
+int vt_set_focal_distance(vt_ctx* c, float d)
+{
+    if (!c) return VT_ERR_INVALID;
+    Shared s; int rc = shared_rw(c, &s, false); if (rc) return rc;
+    s.focal_distance = d; return shared_rw(c, &s, true);
+}
+int vt_get_focal_distance(vt_ctx* c, float* d)
+{
+    if (!c || !d) return VT_ERR_INVALID;
+    Shared s; int rc = shared_rw(c, &s, false); if (rc) return rc;
+    *d = s.focal_distance; return VT_OK;
+}
+int vt_set_selection(vt_ctx* c, const int32_t index[4], const float normal[4])
+{
+    if (!c || !index) return VT_ERR_INVALID;
+    Shared s; int rc = shared_rw(c, &s, false); if (rc) return rc;
+    for (int i = 0; i < 4; ++i) { s.sel_index[i] = index[i]; if (normal) s.sel_normal[i] = normal[i]; }
+    return shared_rw(c, &s, true);
+}
+int vt_get_selection(vt_ctx* c, int32_t index[4], float normal[4])
+{
+    if (!c) return VT_ERR_INVALID;
+    Shared s; int rc = shared_rw(c, &s, false); if (rc) return rc;
+    for (int i = 0; i < 4; ++i) { if (index) index[i] = s.sel_index[i]; if (normal) normal[i] = s.sel_normal[i]; }
+    return VT_OK;
+}
+
+// ---- launch parameter blocks ----------------------------------------------------------------------
+static Volume make_volume(const vt_ctx* c)
+{
+    Volume V;
+    V.mat = c->d_mat; V.bricks = c->d_bricks; V.supers = c->d_supers;
+    V.X = c->X; V.Y = c->Y; V.Z = c->Z;
+    V.BX = c->BX; V.BXY = c->BX * c->BY; V.SX = c->SX; V.SXY = c->SX * c->SY;
+    V.bmin.x = c->bmin[0]; V.bmin.y = c->bmin[1]; V.bmin.z = c->bmin[2];
+    V.bmax.x = c->bmax[0]; V.bmax.y = c->bmax[1]; V.bmax.z = c->bmax[2];
+    V.vsize.x = c->vsize[0]; V.vsize.y = c->vsize[1]; V.vsize.z = c->vsize[2];
+    V.resf.x = (float)c->X; V.resf.y = (float)c->Y; V.resf.z = (float)c->Z;
+    // dda.h:98  int(2 * ceil(length(vec3(voxelResolution)))), binary32, unfused
+    volatile float xx = V.resf.x * V.resf.x, yy = V.resf.y * V.resf.y, zz = V.resf.z * V.resf.z;
+    volatile float s = xx + yy; s = s + zz;
+    V.max_steps = (int)(2.0f * std::ceil(std::sqrt((float)s)));
+    return V;
+}
+
+static Frame make_frame(const vt_ctx* c)
+{
+    Frame F;
+    memcpy(F.inv_mv, c->cam.inv_modelview, sizeof F.inv_mv);
+    memcpy(F.proj, c->cam.proj, sizeof F.proj);
+    memcpy(F.inv_proj, c->cam.inv_proj, sizeof F.inv_proj);
+    F.near_z = c->cam.near_z; F.lens_radius = c->cam.lens_radius; F.lens_model = c->cam.lens_model;
+    F.W = c->st.width; F.H = c->st.height; F.max_bounces = c->st.max_bounces;
+    F.bg_top.x = c->st.bg_top[0]; F.bg_top.y = c->st.bg_top[1]; F.bg_top.z = c->st.bg_top[2];
+    F.bg_bottom.x = c->st.bg_bottom[0]; F.bg_bottom.y = c->st.bg_bottom[1]; F.bg_bottom.z = c->st.bg_bottom[2];
+    F.use_image = (c->st.use_env_image && c->d_env) ? 1 : 0;
+    F.env_rotation = c->st.env_rotation_rad; F.env_integral = c->env_integral;
+    F.wire_opacity = c->st.wireframe_opacity; F.wire_thickness = c->st.wireframe_thickness;
+    F.noise = c->d_noise; F.noise_w = c->noise_w; F.noise_h = c->noise_h;
+    F.materials = c->d_materials; F.n_materials = (int)c->n_materials;
+    F.emissive = c->d_emissive; F.n_emissive = (int)c->n_emissive;
+    F.env = c->d_env; F.env_w = c->env_w; F.env_h = c->env_h;
+    F.cdf_u = c->d_cdf_u; F.cdf_u_w = c->cdf_u_w; F.cdf_u_h = c->cdf_u_h;
+    F.cdf_v = c->d_cdf_v; F.cdf_v_n = c->cdf_v_n;
+    F.shared = c->d_shared;
+    return F;
+}
+
+// ---- rendering ---------------------------------------------------------------------------------------
+int vt_reset_accumulation(vt_ctx* c)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_BIND(c);
+    if (c->d_accum) VT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, c->accum_pixels * sizeof(float4), c->stream));
+    c->num_samples = 0;
+    return VT_OK;
+}
+
+int vt_set_partition(vt_ctx* c, int mode, int rank, int world)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, mode >= VT_PART_NONE && mode <= VT_PART_SAMPLES && world >= 1 && rank >= 0 && rank < world, "bad partition");
+    c->part_mode = (world == 1) ? VT_PART_NONE : mode; c->part_rank = rank; c->part_world = world;
+    return VT_OK;
+}
+
+int vt_enable_primary_hits(vt_ctx* c, int enable) { if (!c) return VT_ERR_INVALID; c->primary_enabled = enable != 0; return VT_OK; }
+int vt_counters_enable(vt_ctx* c, int enable) { if (!c) return VT_ERR_INVALID; c->count_enabled = enable != 0; return VT_OK; }
+
+int vt_render(vt_ctx* c, int first_sample, int n_passes)
+{
+    if (!c) return VT_ERR_INVALID;
+    if (!c->have_cam || !c->have_settings || !c->d_accum) return fail(c, VT_ERR_STATE, "vt_render before vt_set_camera / vt_set_settings");
+    VT_REQ(c, n_passes >= 0, "negative pass count");
+    if (n_passes == 0) return VT_OK;
+    VT_BIND(c);
+    const int W = c->st.width, H = c->st.height;
+    if (c->primary_enabled && !c->d_primary) VT_CUDA(c, cudaMalloc(&c->d_primary, c->accum_pixels * sizeof(int32_t)));
+    RenderLaunch L;
+    L.n_passes = n_passes; L.n_prev = c->num_samples; L.integrator = c->st.integrator;
+    L.tiles_x = (W + kTile - 1) / kTile; L.tiles_y = (H + kTile - 1) / kTile;
+    L.tile_rank = 0; L.tile_world = 1; L.sum_mode = 0; L.first_sample = first_sample; L.sample_stride = 1;
+    if (c->part_mode == VT_PART_TILES) { L.tile_rank = c->part_rank; L.tile_world = c->part_world; }
+    if (c->part_mode == VT_PART_SAMPLES) { L.sum_mode = 1; L.first_sample = first_sample + c->part_rank; L.sample_stride = c->part_world; }
+    const int tiles = L.tiles_x * L.tiles_y;
+    const int my_tiles = (tiles - L.tile_rank + L.tile_world - 1) / L.tile_world;
+    if (my_tiles > 0) {
+        const Volume V = make_volume(c); const Frame F = make_frame(c);
+        const dim3 grid((unsigned)(my_tiles * kCtasPerTile));
+        int* prim = c->primary_enabled ? c->d_primary : nullptr;
+        if (c->count_enabled) vt_render_kernel<true><<<grid, 128, 0, c->stream>>>(V, F, L, c->d_accum, prim, c->d_counters);
+        else vt_render_kernel<false><<<grid, 128, 0, c->stream>>>(V, F, L, c->d_accum, prim, c->d_counters);
+        VT_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+        if (c->count_enabled) c->paths += (uint64_t)n_passes * (uint64_t)W * H / (c->part_mode == VT_PART_TILES ? c->part_world : 1);
+    }
+    c->num_samples += n_passes;
+    return VT_OK;
+}
+
+int vt_get_num_samples(vt_ctx* c, int* n) { if (!c || !n) return VT_ERR_INVALID; *n = c->num_samples; return VT_OK; }
+
+int vt_read_average(vt_ctx* c, float* out)
+{
+    if (!c || !out) return VT_ERR_INVALID;
+    if (!c->d_accum) return fail(c, VT_ERR_STATE, "no frame");
+    VT_BIND(c);
+    VT_CUDA(c, cudaMemcpyAsync(out, c->d_accum, c->accum_pixels * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VT_OK;
+}
+
+int vt_read_primary_hits(vt_ctx* c, int32_t* out)
+{
+    if (!c || !out) return VT_ERR_INVALID;
+    if (!c->d_primary) return fail(c, VT_ERR_STATE, "primary hits not enabled before the last vt_render");
+    VT_BIND(c);
+    VT_CUDA(c, cudaMemcpyAsync(out, c->d_primary, c->accum_pixels * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VT_OK;
+}
+
+void* vt_accum_device_ptr(vt_ctx* c) { return c ? (void*)c->d_accum : nullptr; }
+
+int vt_get_counters(vt_ctx* c, vt_counters* out)
+{
+    if (!c || !out) return VT_ERR_INVALID;
+    VT_BIND(c);
+    Counters h;
+    VT_CUDA(c, cudaMemcpyAsync(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    out->dda_steps = h.S; out->rand_calls = h.R; out->material_evals = h.H; out->cdf_loads = h.E; out->env_lookups = h.Q;
+    out->paths = c->paths; out->kernel_launches = c->launches;
+    return VT_OK;
+}
+int vt_reset_counters(vt_ctx* c)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_BIND(c);
+    VT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->stream));
+    c->paths = 0;
+    return VT_OK;
+}
+
+// ---- voxelizer ----------------------------------------------------------------------------------------
+int vt_voxelize(vt_ctx* c, const float* xyz, size_t n_verts, const uint32_t* indices, size_t n_indices,
+                const float M[16], int X, int Y, int Z, int32_t fill)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, xyz && indices && M && n_indices % 3 == 0, "bad mesh arrays");
+    VT_REQ(c, fill >= 0, "fill offset must be >= 0");
+    for (size_t i = 0; i < n_indices; ++i) VT_REQ(c, indices[i] < n_verts, "vertex index out of range");
+    VT_BIND(c);
+    int rc = alloc_volume(c, X, Y, Z);
+    if (rc != VT_OK) return rc;
+    float* d_xyz = nullptr; unsigned int* d_idx = nullptr; float* d_M = nullptr;
+    VT_CUDA(c, cudaMalloc(&d_xyz, std::max<size_t>(1, n_verts) * 3 * sizeof(float)));
+    VT_CUDA(c, cudaMalloc(&d_idx, std::max<size_t>(1, n_indices) * sizeof(unsigned int)));
+    VT_CUDA(c, cudaMalloc(&d_M, 16 * sizeof(float)));
+    VT_CUDA(c, cudaMemcpyAsync(d_xyz, xyz, n_verts * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    VT_CUDA(c, cudaMemcpyAsync(d_idx, indices, n_indices * sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));
+    VT_CUDA(c, cudaMemcpyAsync(d_M, M, 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    const size_t nb = (size_t)c->BX * c->BY * c->BZ, ns = (size_t)c->SX * c->SY * c->SZ;
+    const int n_tris = (int)(n_indices / 3);
+    // timed region: clear + scatter + derive (kernel time incl. grid clear, excl. OBJ parse and H2D)
+    VT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    VT_CUDA(c, cudaMemsetAsync(c->d_bricks, 0, nb * 8, c->stream));
+    VT_CUDA(c, cudaMemsetAsync(c->d_supers, 0, ns * 8, c->stream));
+    if (n_tris > 0) {
+        const int ctas = std::max(1, std::min((n_tris + 3) / 4, 148 * 16));
+        vt_voxelize_kernel<<<ctas, 128, 0, c->stream>>>(d_xyz, d_idx, n_tris, d_M, X, Y, Z, c->BX, c->BX * c->BY, c->d_bricks);
+        c->launches += 1;
+    }
+    vt_build_supers_kernel<<<grid_for(nb, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_supers, c->BX, c->BY, c->BZ, c->SX, c->SX * c->SY);
+    vt_fill_offsets_kernel<<<grid_for((size_t)c->BX * Y * Z, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_mat, X, Y, Z, c->BX, c->BX * c->BY, fill);
+    c->launches += 2;
+    VT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    VT_CUDA(c, cudaGetLastError());
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    VT_CUDA(c, cudaEventElapsedTime(&c->last_voxelize_ms, c->ev0, c->ev1));
+    cudaFree(d_xyz); cudaFree(d_idx); cudaFree(d_M);
+    return VT_OK;
+}
+
+int vt_get_last_voxelize_ms(vt_ctx* c, float* ms) { if (!c || !ms) return VT_ERR_INVALID; *ms = c->last_voxelize_ms; return VT_OK; }
+
+int vt_volume_assign_materials(vt_ctx* c, const int32_t* table, int n_table, int rule)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, table && n_table > 0 && rule == 1, "bad material rule");
+    VT_BIND(c);
+    int* d_table = nullptr;
+    VT_CUDA(c, cudaMalloc(&d_table, n_table * sizeof(int)));
+    VT_CUDA(c, cudaMemcpyAsync(d_table, table, n_table * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    const size_t n = (size_t)c->X * c->Y * c->Z;
+    vt_assign_materials_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->d_mat, c->X, c->Y, c->Z, d_table, n_table, rule);
+    c->launches += 1;
+    VT_CUDA(c, cudaGetLastError());
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_table);
+    return VT_OK;
+}
+
+// ---- services -------------------------------------------------------------------------------------------
+static int need_frame(vt_ctx* c)
+{
+    if (!c->have_cam || !c->have_settings) return fail(c, VT_ERR_STATE, "service called before vt_set_camera / vt_set_settings");
+    return VT_OK;
+}
+int vt_pick(vt_ctx* c, float px, float py)
+{
+    if (!c) return VT_ERR_INVALID;
+    int rc = need_frame(c); if (rc) return rc;
+    VT_BIND(c);
+    vt_pick_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), make_frame(c), px, py, c->d_shared);
+    c->launches += 1;
+    VT_CUDA(c, cudaGetLastError());
+    return VT_OK;
+}
+int vt_pick_focal(vt_ctx* c, float px, float py)
+{
+    if (!c) return VT_ERR_INVALID;
+    int rc = need_frame(c); if (rc) return rc;
+    VT_BIND(c);
+    vt_pick_focal_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), make_frame(c), px, py, c->d_shared);
+    c->launches += 1;
+    VT_CUDA(c, cudaGetLastError());
+    return VT_OK;
+}
+int vt_add_voxel(vt_ctx* c, float mx, float my)
+{
+    if (!c) return VT_ERR_INVALID;
+    int rc = need_frame(c); if (rc) return rc;
+    VT_BIND(c);
+    vt_add_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), make_frame(c), mx, my, c->d_shared, c->d_mat, c->d_bricks, c->d_supers, c->d_result);
+    c->launches += 1;
+    VT_CUDA(c, cudaGetLastError());
+    return VT_OK;
+}
+int vt_remove_voxel(vt_ctx* c)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_BIND(c);
+    vt_remove_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), c->d_shared, c->d_mat, c->d_bricks, c->d_supers, c->d_result);
+    c->launches += 1;
+    VT_CUDA(c, cudaGetLastError());
+    return VT_OK;
+}
+
+int vt_debug_trace_rays(vt_ctx* c, const float* rays, size_t n, float* out)
+{
+    if (!c || !rays || !out) return VT_ERR_INVALID;
+    if (n == 0) return VT_OK;
+    VT_BIND(c);
+    float *d_r = nullptr, *d_o = nullptr;
+    VT_CUDA(c, cudaMalloc(&d_r, n * 6 * sizeof(float)));
+    VT_CUDA(c, cudaMalloc(&d_o, n * 4 * sizeof(float)));
+    VT_CUDA(c, cudaMemcpyAsync(d_r, rays, n * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    vt_trace_rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(make_volume(c), d_r, n, d_o);
+    c->launches += 1;
+    VT_CUDA(c, cudaGetLastError());
+    VT_CUDA(c, cudaMemcpyAsync(out, d_o, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_r); cudaFree(d_o);
+    return VT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,707 @@
+// vt_device.cuh -- device-side data layout and the shared device functions of the
+// path tracer: ray generation, slab test, DDA traversal, hit frame, BSDFs, lights.
+// Each function cites the reference shader it implements (paths relative to
+// /root/reference/src/shaders). Arithmetic contract: vt_math.cuh.
+#pragma once
+#include "vt_math.cuh"
+
+namespace vt {
+
+// ----------------------------------------------------------------------------------
+// HBM layout of one scene (all pointers are device pointers owned by vt_ctx)
+// ----------------------------------------------------------------------------------
+// Occupancy is bit-packed in 4x4x4 bricks: one uint64 per brick, bit (x&3)|(y&3)<<2|(z&3)<<4,
+// bricks x-fastest. One level up, a "super" word per 4x4x4 bricks (16^3 voxels) holds one
+// bit per brick = "brick is not empty"; the DDA reads a brick word only when its super bit
+// is set, so traversal of empty space touches 1/4096 of the voxels' worth of memory and the
+// per-step arithmetic (identical to dda.h) runs out of registers.
+// The int32 material-offset grid of the reference (R32I, x fastest, -1 empty) is kept as is
+// and read once per surface hit.
+struct Volume {
+    const int32_t* __restrict__ mat;       // X*Y*Z material offsets
+    const unsigned long long* __restrict__ bricks;
+    const unsigned long long* __restrict__ supers;
+    int X, Y, Z;
+    int BX, BXY;                           // brick grid strides
+    int SX, SXY;                           // super grid strides
+    f3 bmin, bmax, vsize, resf;            // world bounds, wsVoxelSize, vec3(voxelResolution)
+    int max_steps;                         // dda.h:98
+};
+
+// state the reference keeps in two SSBOs (focalDistanceDevice.h, selectVoxelDevice.h)
+struct Shared {
+    float focal_distance;
+    int sel_index[4];
+    float sel_normal[4];
+};
+
+struct Frame {
+    float inv_mv[16], proj[16], inv_proj[16];
+    float near_z;
+    float lens_radius;
+    int lens_model;
+    int W, H;
+    int max_bounces;
+    f3 bg_top, bg_bottom;
+    int use_image;
+    float env_rotation, env_integral;
+    float wire_opacity, wire_thickness;
+    const float4* __restrict__ noise; int noise_w, noise_h;
+    const float* __restrict__ materials; int n_materials;
+    const int32_t* __restrict__ emissive; int n_emissive;
+    const float4* __restrict__ env; int env_w, env_h;       // rgb padded to float4
+    const float* __restrict__ cdf_u; int cdf_u_w, cdf_u_h;
+    const float* __restrict__ cdf_v; int cdf_v_n;
+    const Shared* __restrict__ shared;
+};
+
+struct Basis { f3 position, tangent, normal, binormal; };   // coordinates.h:35-41
+
+struct Counters { unsigned long long S, R, H, E, Q; };
+
+template <bool COUNT> struct Tally {
+    unsigned int S, R, H, E, Q;
+    VT_DEV void clear() { S = R = H = E = Q = 0; }
+};
+
+#define VT_TALLY(field, n) do { if (COUNT) tl.field += (n); } while (0)
+
+// ----------------------------------------------------------------------------------
+// random.h
+// ----------------------------------------------------------------------------------
+VT_DEV int wang_hash(int seed)                                   // random.h:3-11
+{
+    seed = (seed ^ 61) ^ (seed >> 16);
+    seed = (int)((unsigned)seed * 9u);
+    seed = seed ^ (seed >> 4);
+    seed = (int)((unsigned)seed * 0x27d4eb2du);
+    seed = seed ^ (seed >> 15);
+    return seed;
+}
+VT_DEV int2 rng_offset(int px, int py, int sequence, int rw, int rh)   // random.h:13-18
+{
+    const int offset = wang_hash((int)((unsigned)px + (unsigned)py * (unsigned)rw)) ^ wang_hash(sequence);
+    return make_int2(offset % rw, (offset / rw) % rh);
+}
+template <bool COUNT>
+VT_DEV f4 rng_next(const Frame& F, int2& off, Tally<COUNT>& tl)        // random.h:20-27
+{
+    f4 r = mk4(0.f, 0.f, 0.f, 0.f);
+    if (off.x >= 0 && off.y >= 0 && off.x < F.noise_w && off.y < F.noise_h) {
+        const float4 t = __ldg(F.noise + ((size_t)off.x + (size_t)off.y * (size_t)F.noise_w));
+        r = mk4(t.x, t.y, t.z, t.w);
+    }
+    off.x = (off.x + 1) % F.noise_w;
+    if (off.x == 0) off.y = (off.y + 1) % F.noise_h;
+    VT_TALLY(R, 1);
+    return r;
+}
+
+// ----------------------------------------------------------------------------------
+// aabb.h:1-32
+// ----------------------------------------------------------------------------------
+VT_DEV float ray_aabb(f3 o, f3 d, f3 bmin, f3 bmax)
+{
+    const f3 inv = mk3(1.0f) / d;
+    const f3 t0 = (bmin - o) * inv;
+    const f3 t1 = (bmax - o) * inv;
+    const f3 tmin = gmin(t0, t1);
+    const float tminf = gmax(tmin.x, gmax(tmin.y, tmin.z));
+    const f3 tmax = gmax(t0, t1);
+    const float tmaxf = gmin(tmax.x, gmin(tmax.y, tmax.z));
+    if (tmaxf < 0.0f) return -1.0f;
+    if (tminf > tmaxf) return -1.0f;
+    return gmax(0.0f, tminf);
+}
+
+// ----------------------------------------------------------------------------------
+// dda.h
+// ----------------------------------------------------------------------------------
+VT_DEV bool out_of_grid(f3 p, f3 resf)
+{
+    return (p.x < 0.0f) || (p.y < 0.0f) || (p.z < 0.0f) || (p.x >= resf.x) || (p.y >= resf.y) || (p.z >= resf.z);
+}
+VT_DEV int fetch_offset(const Volume& V, int x, int y, int z)     // texelFetch(materialOffsetTexture); out of range -> 0
+{
+    if ((unsigned)x >= (unsigned)V.X || (unsigned)y >= (unsigned)V.Y || (unsigned)z >= (unsigned)V.Z) return 0;
+    return __ldg(V.mat + ((size_t)x + (size_t)y * (size_t)V.X + (size_t)z * (size_t)V.X * (size_t)V.Y));
+}
+
+// Literal float-state restatement of dda.h:38-57, used only when the start voxel is NaN
+// (the integer-state loop below cannot represent it). Never taken by finite rays.
+template <bool COUNT>
+__device__ __noinline__ bool raymarch_slow(const Volume& V, f3 vp, f3 dis, f3 sg, f3 inc, f3& hit_pos, Tally<COUNT>& tl)
+{
+    bool isect = false;
+    for (int steps = 0; steps < V.max_steps; ++steps) {
+        if (out_of_grid(vp, V.resf)) break;
+        VT_TALLY(S, 1);
+        if (fetch_offset(V, f2i(vp.x), f2i(vp.y), f2i(vp.z)) >= 0) { isect = true; break; }
+        const f3 mask = mk3(gstep(dis.x, dis.y) * gstep(dis.x, dis.z),
+                            gstep(dis.y, dis.x) * gstep(dis.y, dis.z),
+                            gstep(dis.z, dis.y) * gstep(dis.z, dis.x));
+        dis = dis + (mask * sg) * inc;
+        vp = vp + mask * sg;
+    }
+    hit_pos = vp;
+    return isect;
+}
+
+// dda.h:7-61. hit_pos is zero on the early-out path (contract U1).
+template <bool COUNT>
+VT_DEV bool raymarch(const Volume& V, f3 o, f3 d, f3& hit_pos, Tally<COUNT>& tl)
+{
+    hit_pos = mk3(0.0f);
+    const f3 ext = mk3(1.0f) / (V.bmax - V.bmin);                 // :16
+    o = o + gsign(d) * 0.001f;                                    // :19
+    const f3 vo = ((o - V.bmin) * ext) * V.resf;                  // :20
+    const f3 vp = gfloor(vo);                                     // :22
+    if (out_of_grid(vp, V.resf)) return false;                    // :24-25
+    // :29  mix(d, 1e-5, step(abs(d), 1e-5))
+    d = mk3(gmix(d.x, 1e-5f, gstep(gabs(d.x), 1e-5f)),
+            gmix(d.y, 1e-5f, gstep(gabs(d.y), 1e-5f)),
+            gmix(d.z, 1e-5f, gstep(gabs(d.z), 1e-5f)));
+    const f3 inc = mk3(1.0f) / d;                                 // :31
+    const f3 sg = gsign(d);                                       // :32
+    f3 dis = (((vp - vo) + 0.5f) + sg * 0.5f) * inc;              // :34
+
+    if (vp.x != vp.x || vp.y != vp.y || vp.z != vp.z)             // NaN start voxel passes the bounds test of :24
+        return raymarch_slow<COUNT>(V, vp, dis, sg, inc, hit_pos, tl);
+
+    // Integer voxel coordinates (exact: 0 <= vp < res) and per-axis increments.
+    // (mask*sign)*inc of dda.h:52 is +-inc = |1/d| for a stepping axis and +-0 otherwise.
+    int ix = f2i(vp.x), iy = f2i(vp.y), iz = f2i(vp.z);
+    const int sx = f2i(sg.x), sy = f2i(sg.y), sz = f2i(sg.z);
+    const float ex = sg.x * inc.x, ey = sg.y * inc.y, ez = sg.z * inc.z;
+    float dx = dis.x, dy = dis.y, dz = dis.z;
+
+    bool isect = false;
+    int bkey = -1, skey = -1;
+    unsigned long long brick = 0ull, super = 0ull;
+    int steps = 0;
+    const int max_steps = V.max_steps;
+    while (steps < max_steps) {                                   // :38
+        if ((unsigned)ix >= (unsigned)V.X || (unsigned)iy >= (unsigned)V.Y || (unsigned)iz >= (unsigned)V.Z) break; // :41-42
+        const int bx = ix >> 2, by = iy >> 2, bz = iz >> 2;
+        const int key = bx + by * V.BX + bz * V.BXY;
+        if (key != bkey) {
+            bkey = key;
+            const int sk = (bx >> 2) + (by >> 2) * V.SX + (bz >> 2) * V.SXY;
+            if (sk != skey) { skey = sk; super = __ldg(V.supers + sk); }
+            const int sbit = (bx & 3) | ((by & 3) << 2) | ((bz & 3) << 4);
+            brick = ((super >> sbit) & 1ull) ? __ldg(V.bricks + key) : 0ull;
+        }
+        VT_TALLY(S, 1);
+        const int bit = (ix & 3) | ((iy & 3) << 2) | ((iz & 3) << 4);
+        if ((brick >> bit) & 1ull) { isect = true; break; }       // :44-50
+        // :51 mask = step(dis.xyz, dis.yxy) * step(dis.xyz, dis.zzx)   (ties step several axes)
+        const bool mx = !(dy < dx) && !(dz < dx);
+        const bool my = !(dx < dy) && !(dz < dy);
+        const bool mz = !(dy < dz) && !(dx < dz);
+        if (mx) { dx = dx + ex; ix += sx; }                        // :52-53
+        if (my) { dy = dy + ey; iy += sy; }
+        if (mz) { dz = dz + ez; iz += sz; }
+        ++steps;
+    }
+    hit_pos = mk3((float)ix, (float)iy, (float)iz);               // :59
+    return isect;
+}
+
+// dda.h:63-100
+template <bool COUNT>
+VT_DEV bool traverse(const Volume& V, f3 o, f3 d, f3& hit_pos, bool& hit_ground, Tally<COUNT>& tl)
+{
+    if (raymarch<COUNT>(V, o, d, hit_pos, tl)) { hit_ground = false; return true; }
+    hit_ground = (hit_pos.y < 0.0f);
+    return hit_ground;
+}
+
+// ----------------------------------------------------------------------------------
+// coordinates.h
+// ----------------------------------------------------------------------------------
+VT_DEV f4 screen_to_eye_persp(const Frame& F, f3 ws)              // coordinates.h:12-27
+{
+    const float vx = 0.0f, vy = 0.0f, vz = (float)F.W, vw = (float)F.H;
+    f3 ndc;
+    ndc.x = ((2.0f * ws.x) - (2.0f * vx)) / vz - 1.0f;
+    ndc.y = ((2.0f * ws.y) - (2.0f * vy)) / vw - 1.0f;
+    ndc.z = (2.0f * ws.z - 0.0f - 1.0f) / (1.0f - 0.0f);
+    // GLSL cameraProj[3][2] = host pm.x[2][3], [2][2] = pm.x[2][2], [2][3] = pm.x[3][2]
+    const float cw = F.proj[11] / (ndc.z - (F.proj[10] / F.proj[14]));
+    return mul44(F.inv_proj, ndc.x * cw, ndc.y * cw, ndc.z * cw, cw);
+}
+VT_DEV f4 screen_to_eye_ortho(const Frame& F, f3 ws)              // coordinates.h:1-10
+{
+    f3 ndc;
+    ndc.x = (ws.x / (float)F.W) * 2.0f - 1.0f;
+    ndc.y = (ws.y / (float)F.H) * 2.0f - 1.0f;
+    ndc.z = (2.0f * ws.z - 0.0f - 1.0f) / (1.0f - 0.0f);
+    return mul44(F.inv_proj, ndc.x, ndc.y, ndc.z, 1.0f);
+}
+VT_DEV f3 local_to_world(f3 v, const Basis& b)                    // coordinates.h:43-49
+{
+    return (v.x * b.tangent + v.y * b.normal) + v.z * b.binormal;
+}
+VT_DEV f3 world_to_local(f3 v, const Basis& b)                    // coordinates.h:51-57
+{
+    return mk3(dot(v, b.tangent), dot(v, b.normal), dot(v, b.binormal));
+}
+VT_DEV void voxel_to_world(const Volume& V, f3 vsP, f3 o, f3 d, Basis& b)   // coordinates.h:59-82
+{
+    const f3 vmin = vsP * V.vsize + V.bmin;
+    const f3 vmax = vmin + V.vsize;
+    const float t = ray_aabb(o, d, vmin, vmax);
+    b.position = o + d * t;
+    const f3 center = vmin + V.vsize * 0.5f;
+    const f3 h = b.position - center;
+    const f3 a = gabs(h);
+    const f3 mask = mk3(gstep(a.y, a.x) * gstep(a.z, a.x),
+                        gstep(a.x, a.y) * gstep(a.z, a.y),
+                        gstep(a.x, a.z) * gstep(a.y, a.z));
+    b.normal = mask * gsign(h);
+    const f3 tan0 = cross(b.normal, mk3(0.57735026919f));
+    b.binormal = normalize(cross(tan0, b.normal));
+    b.tangent = normalize(cross(b.binormal, b.normal));
+}
+VT_DEV f3 spherical(float phi, float cosT, float sinT)            // coordinates.h:91-95
+{
+    float s, c; gsincos(phi, s, c);
+    return mk3(sinT * c, cosT, sinT * s);
+}
+VT_DEV f2 uv_from_vector(f3 v, float rot)                         // coordinates.h:97-109
+{
+    const float theta = gacos(v.y);
+    const float phi = gatan2(v.z, v.x) + VT_PI + rot;
+    return mk2(gmod(phi / VT_TWO_PI, 1.0f), theta / VT_PI);
+}
+VT_DEV f3 direction_from_uv(f2 uv, float rot)                     // coordinates.h:111-116 + :85-89
+{
+    const float phi = uv.x * VT_TWO_PI - VT_PI - rot;
+    const float theta = uv.y * VT_PI;
+    float st, ct; gsincos(theta, st, ct);
+    float sp, cp; gsincos(phi, sp, cp);
+    return mk3(st * cp, ct, st * sp);
+}
+
+// ----------------------------------------------------------------------------------
+// sampling.h
+// ----------------------------------------------------------------------------------
+VT_DEV f2 sample_disk(float ux, float uy)                         // sampling.h:2-7
+{
+    const float r = sqrtf(ux);
+    const float theta = 2.0f * VT_PI * uy;
+    float s, c; gsincos(theta, s, c);
+    return mk2(r * c, r * s);
+}
+VT_DEV f4 cosine_hemisphere(float ux, float uy)                   // sampling.h:13-22
+{
+    const f2 p = sample_disk(ux, uy);
+    const float y = sqrtf(gmax(0.0f, 1.0f - p.x * p.x - p.y * p.y));
+    return mk4(p.x, y, p.y, y / VT_PI);
+}
+VT_DEV f4 uniform_hemisphere(float ux, float uy)                  // sampling.h:27-36
+{
+    const float y = ux;
+    const float r = sqrtf(gmax(0.0f, 1.0f - y * y));
+    const float phi = uy * 2.0f * VT_PI;
+    float s, c; gsincos(phi, s, c);
+    return mk4(r * c, y, r * s, 1.0f / (2.0f * VT_PI));
+}
+VT_DEV float power_heuristic(float f, float g) { return f * f / (f * f + g * g); }   // sampling.h:40-43
+
+// ----------------------------------------------------------------------------------
+// generateRay.h
+// ----------------------------------------------------------------------------------
+VT_DEV void pinhole_ray(const Frame& F, f3 frag, float ux, float uy, f3& ro, f3& rd)   // generateRay.h:10-26
+{
+    const f3 jitter = mk3(ux - 0.5f, uy - 0.5f, 0.0f);
+    const f4 es = screen_to_eye_persp(F, frag + jitter);
+    const f4 o = mul44(F.inv_mv, 0.0f, 0.0f, 0.0f, 1.0f);
+    const f3 n = normalize(xyz(es));
+    const f4 d = mul44(F.inv_mv, n.x, n.y, n.z, 0.0f);
+    const float len = sqrtf(((d.x * d.x + d.y * d.y) + d.z * d.z) + d.w * d.w);     // normalize(vec4)
+    ro = xyz(o);
+    rd = mk3(d.x / len, d.y / len, d.z / len);
+}
+template <bool COUNT>
+VT_DEV void generate_ray(const Frame& F, f3 frag, int2& rng, f3& ro, f3& rd, Tally<COUNT>& tl)   // generateRay.h:104-123
+{
+    if (F.lens_model == 0) {
+        const f4 u = rng_next<COUNT>(F, rng, tl);
+        pinhole_ray(F, frag, u.x, u.y, ro, rd);
+    } else if (F.lens_model == 1) {                               // generateRay.h:30-101
+        const float fd = F.shared->focal_distance;
+        const f4 u = rng_next<COUNT>(F, rng, tl);
+        const f2 disk = sample_disk(u.x, u.y);
+        const f3 es = xyz(screen_to_eye_persp(F, frag));
+        const f3 esd = normalize(es);
+        const float t = fd / -(esd.z);
+        const f3 focal = es + t * esd;
+        const f4 fp = mul44(F.inv_mv, focal.x, focal.y, focal.z, 1.0f);
+        const f4 o = mul44(F.inv_mv, disk.x * F.lens_radius, disk.y * F.lens_radius, 0.0f, 1.0f);
+        ro = xyz(o);
+        rd = normalize(xyz(fp) - ro);
+    } else {                                                      // generateRay.h:1-7
+        const f4 e = screen_to_eye_ortho(F, frag);
+        ro = xyz(mul44(F.inv_mv, e.x, e.y, e.z, e.w));
+        rd = xyz(mul44(F.inv_mv, 0.0f, 0.0f, -1.0f, 0.0f));
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// lights.h, color.h, envLight/envMapSample.h
+// ----------------------------------------------------------------------------------
+VT_DEV float luminance(f3 c) { return dot(c, mk3(0.2126f, 0.7152f, 0.0722f)); }      // color.h:1-8
+
+// texture(backgroundTexture, uv).rgb: GL_LINEAR, clamp-to-edge (renderer.cpp:987-1002)
+template <bool COUNT>
+VT_DEV f3 env_lookup(const Frame& F, f2 uv, Tally<COUNT>& tl)
+{
+    const int w = F.env_w, h = F.env_h;
+    const float x = uv.x * (float)w - 0.5f, y = uv.y * (float)h - 0.5f;
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float a = x - x0f, b = y - y0f;
+    int x0 = f2i(x0f), y0 = f2i(y0f);
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = max(0, min(x0, w - 1)); x1 = max(0, min(x1, w - 1));
+    y0 = max(0, min(y0, h - 1)); y1 = max(0, min(y1, h - 1));
+    const float4 p00 = __ldg(F.env + ((size_t)x0 + (size_t)y0 * w));
+    const float4 p10 = __ldg(F.env + ((size_t)x1 + (size_t)y0 * w));
+    const float4 p01 = __ldg(F.env + ((size_t)x0 + (size_t)y1 * w));
+    const float4 p11 = __ldg(F.env + ((size_t)x1 + (size_t)y1 * w));
+    const f3 top = mk3(gmix(p00.x, p10.x, a), gmix(p00.y, p10.y, a), gmix(p00.z, p10.z, a));
+    const f3 bot = mk3(gmix(p01.x, p11.x, a), gmix(p01.y, p11.y, a), gmix(p01.z, p11.z, a));
+    VT_TALLY(Q, 1);
+    return mk3(gmix(top.x, bot.x, b), gmix(top.y, bot.y, b), gmix(top.z, bot.z, b));
+}
+template <bool COUNT>
+VT_DEV f3 background_color(const Frame& F, f3 v, Tally<COUNT>& tl)                   // lights.h:4-17
+{
+    if (F.use_image != 0) return env_lookup<COUNT>(F, uv_from_vector(v, F.env_rotation), tl);
+    const float bias = gmax(0.0f, v.y);
+    return F.bg_bottom * (1.0f - bias) + F.bg_top * bias;
+}
+template <bool COUNT>
+VT_DEV f4 evaluate_env(const Frame& F, f3 wi, Tally<COUNT>& tl)                      // lights.h:20-33
+{
+    const f3 L = background_color<COUNT>(F, wi, tl);
+    const float pdf = (F.use_image != 0) ? luminance(L) / F.env_integral : 1.0f / (4.0f * VT_PI);
+    return mk4(L, pdf);
+}
+template <bool COUNT>
+VT_DEV float cdf_u_at(const Frame& F, int x, int y, Tally<COUNT>& tl)
+{
+    VT_TALLY(E, 1);
+    if ((unsigned)x >= (unsigned)F.cdf_u_w || (unsigned)y >= (unsigned)F.cdf_u_h) return 0.0f;
+    return __ldg(F.cdf_u + ((size_t)x + (size_t)y * F.cdf_u_w));
+}
+template <bool COUNT>
+VT_DEV float cdf_v_at(const Frame& F, int i, Tally<COUNT>& tl)
+{
+    VT_TALLY(E, 1);
+    if ((unsigned)i >= (unsigned)F.cdf_v_n) return 0.0f;
+    return __ldg(F.cdf_v + i);
+}
+template <bool COUNT>
+VT_DEV f2 sample_env_texture(const Frame& F, float su, float sv, Tally<COUNT>& tl)   // envMapSample.h:23-123
+{
+    const int sizeU = F.cdf_u_w, sizeV = F.cdf_v_n;
+    int lo = 0, hi = sizeV - 1;
+    while (lo != hi - 1) {                                        // :70-94
+        const int m = (lo + hi) / 2;
+        if (sv < cdf_v_at<COUNT>(F, m, tl)) hi = m; else lo = m;
+    }
+    const int row = lo;
+    lo = 0; hi = sizeU - 1;
+    while (lo != hi - 1) {                                        // :98-123
+        const int m = (lo + hi) / 2;
+        if (su < cdf_u_at<COUNT>(F, m, row, tl)) hi = m; else lo = m;
+    }
+    const int col = lo;
+    float cl = cdf_u_at<COUNT>(F, col, row, tl), cu = cdf_u_at<COUNT>(F, col + 1, row, tl);   // :52-54
+    const float du = (su - cl) / (cu - cl);
+    cl = cdf_v_at<COUNT>(F, row, tl); cu = cdf_v_at<COUNT>(F, row + 1, tl);                    // :56-58
+    const float dv = (sv - cl) / (cu - cl);
+    return mk2(((float)col + du) / (float)(sizeU - 1), ((float)row + dv) / (float)(sizeV - 1)); // :61-62
+}
+template <bool COUNT>
+VT_DEV f3 sample_env(const Frame& F, const Basis& b, float ux, float uy, f4& w_pdf, Tally<COUNT>& tl)   // lights.h:36-55
+{
+    if (F.use_image != 0) {
+        const f2 uv = sample_env_texture<COUNT>(F, ux, uy, tl);
+        const f3 w = direction_from_uv(uv, F.env_rotation);
+        const f3 L = env_lookup<COUNT>(F, uv, tl);
+        w_pdf = mk4(w, luminance(L) / F.env_integral);
+        return L;
+    }
+    const f4 l = uniform_hemisphere(ux, uy);
+    w_pdf = mk4(local_to_world(xyz(l), b), l.w);
+    return background_color<COUNT>(F, xyz(w_pdf), tl);
+}
+
+// ----------------------------------------------------------------------------------
+// bsdf/microfacet.h, bsdf/lambertian.h, materials/*.h
+// ----------------------------------------------------------------------------------
+#define VT_IOR 7.3f                                               // microfacet.h:2
+
+VT_DEV float mf_G(f3 wo, f3 wi, f3 wh)                            // microfacet.h:5-15
+{
+    const float NdotWh = wh.y, NdotWo = wo.y, NdotWi = wi.y;
+    const float WoDotWh = gabs(dot(wo, wh));
+    return gmin(1.0f, gmin((2.0f * NdotWh * NdotWo / WoDotWh), (2.0f * NdotWh * NdotWi / WoDotWh)));
+}
+VT_DEV f4 mf_D(f3 refl, float e, f3 wo, f3 wh)                    // microfacet.h:19-37
+{
+    const float powCos = gpow(wh.y, e);
+    const float f = (e + 2.0f) * VT_INV_TWOPI * powCos;
+    const float woDotWh = dot(wo, wh);
+    const float pdf = (woDotWh <= 0.0f) ? 0.0f : ((e + 1.0f) * powCos) / (VT_TWO_PI * 4.0f * woDotWh);
+    return mk4(refl * f, pdf);
+}
+VT_DEV float mf_F(float cosH)                                     // microfacet.h:64-69
+{
+    const float sqrtR0 = (1.0f - VT_IOR) / (1.0f + VT_IOR);
+    const float r0 = sqrtR0 * sqrtR0;
+    return r0 + (1.0f - r0) * gpow(1.0f - cosH, 5.0f);
+}
+VT_DEV f4 eval_microfacet(f3 refl, float e, f3 wo, f3 wi)         // microfacet.h:73-91
+{
+    const float cosWi = wi.y, cosWo = wo.y;
+    const f3 wh = normalize(wi + wo);
+    const float cosH = dot(wi, wh);
+    f4 fp = mf_D(refl, e, wo, wh);
+    const float k = mf_G(wo, wi, wh) * mf_F(cosH) / (4.0f * cosWo * cosWi);
+    fp.x *= k; fp.y *= k; fp.z *= k;
+    return fp;
+}
+VT_DEV f3 sample_microfacet(f3 refl, float e, f3 wo, float ux, float uy, f4& f_pdf)   // microfacet.h:102-123 (+ sampleD :41-61)
+{
+    const float cosT = gpow(ux, 1.0f / (e + 1.0f));
+    const float sinT = sqrtf(gmax(0.0f, 1.0f - cosT * cosT));
+    const float phi = uy * 2.0f * VT_PI;
+    const f3 wh0 = spherical(phi, cosT, sinT);
+    const f3 wi = -wo + (2.0f * dot(wo, wh0)) * wh0;
+    f4 fp = mf_D(refl, e, wo, wh0);
+    const float cosWi = wi.y, cosWo = wo.y;
+    const f3 wh = normalize(wi + wo);
+    const float cosH = dot(wi, wh);
+    const float g = mf_G(wo, wi, wh), f = mf_F(cosH), den = 4.0f * cosWo * cosWi;
+    fp.x = refl.x * fp.x * g * f / den;                           // :116-120
+    fp.y = refl.y * fp.y * g * f / den;
+    fp.z = refl.z * fp.z * g * f / den;
+    f_pdf = fp;
+    return wi;
+}
+
+VT_DEV float fetch_mat(const Frame& F, int i)                     // texelFetch(materialDataTexture); out of range -> 0
+{
+    if ((unsigned)i >= (unsigned)F.n_materials) return 0.0f;
+    return __ldg(F.materials + i);
+}
+VT_DEV f3 mat_vec(const Frame& F, int off) { return mk3(fetch_mat(F, off), fetch_mat(F, off + 1), fetch_mat(F, off + 2)); }
+
+template <bool COUNT>
+VT_DEV f4 evaluate_material(const Frame& F, int off, f3 wo, f3 wi, Tally<COUNT>& tl)  // materials.h:7-19
+{
+    const int type = f2i(fetch_mat(F, off));
+    VT_TALLY(H, 1);
+    off += 1;
+    switch (type) {
+    case 0: { const f3 a = mat_vec(F, off + 3); return mk4(a / VT_PI, wi.y / VT_PI); }               // matte.h:1-10, lambertian.h:23-29
+    case 1: return eval_microfacet(mat_vec(F, off + 3), fetch_mat(F, off + 6), wo, wi);               // metal.h:1-17
+    case 2: return eval_microfacet(mk3(1.0f), fetch_mat(F, off + 6), wo, wi);                         // plastic.h:1-17
+    default: return mk4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <bool COUNT>
+VT_DEV f3 sample_material(const Frame& F, int off, f3 wo, int2& rng, f4& f_pdf, Tally<COUNT>& tl)     // materials.h:30-43
+{
+    const int type = f2i(fetch_mat(F, off));
+    VT_TALLY(H, 1);
+    off += 1;
+    switch (type) {
+    case 0: {                                                     // matte.h:12-22, lambertian.h:10-19
+        const f3 a = mat_vec(F, off + 3);
+        const f4 u = rng_next<COUNT>(F, rng, tl);
+        const f4 l = cosine_hemisphere(u.x, u.y);
+        f_pdf = mk4(a / VT_PI, l.w);
+        return xyz(l);
+    }
+    case 1: { const f4 u = rng_next<COUNT>(F, rng, tl);           // metal.h:19-36
+              return sample_microfacet(mat_vec(F, off + 3), fetch_mat(F, off + 6), wo, u.x, u.y, f_pdf); }
+    case 2: { const f4 u = rng_next<COUNT>(F, rng, tl);           // plastic.h:19-28
+              return sample_microfacet(mk3(1.0f), fetch_mat(F, off + 6), wo, u.x, u.y, f_pdf); }
+    default: f_pdf = mk4(0.f, 0.f, 0.f, 0.f); return mk3(0.0f);
+    }
+}
+template <bool COUNT>
+VT_DEV f3 emission_material(const Frame& F, int off, Tally<COUNT>& tl)                 // materials.h:46-56
+{
+    const int type = f2i(fetch_mat(F, off));
+    VT_TALLY(H, 1);
+    if (type == 0 || type == 1 || type == 2) return mat_vec(F, off + 1);
+    return mk3(0.0f);
+}
+
+// ----------------------------------------------------------------------------------
+// integrator pieces shared by pathTracer.fs and editMode.fs
+// ----------------------------------------------------------------------------------
+VT_DEV void voxel_index_to_pos(int idx, int X, int Y, int& x, int& y, int& z)          // coordinates.h:118-128
+{
+    const int dz = X * Y, dy = X;
+    z = idx / dz; idx -= z * dz;
+    y = idx / dy; idx -= y * dy;
+    x = idx;
+}
+
+template <bool COUNT>
+VT_DEV f3 direct_lighting(const Volume& V, const Frame& F, int mat_off, const Basis& hb, f3 wo, int2& rng, Tally<COUNT>& tl)   // pathTracer.fs:64-170
+{
+    f4 wl = mk4(0.f, 0.f, 0.f, 0.f);
+    f3 L;
+    int ex = 0, ey = 0, ez = 0;
+    const f4 u = rng_next<COUNT>(F, rng, tl);                     // :77
+    const int num_lights = F.n_emissive + 1;                      // :78
+    const int light_index = f2i(u.x * (float)num_lights);         // :79
+    const bool sampling_voxel = light_index < num_lights - 1;     // :81
+    if (sampling_voxel) {
+        const int eidx = __ldg(F.emissive + light_index);         // :85
+        voxel_index_to_pos(eidx, V.X, V.Y, ex, ey, ez);           // :86
+        const int eoff = fetch_offset(V, ex, ey, ez);             // :87
+        L = mk3(10.0f) * emission_material<COUNT>(F, eoff, tl);   // :88
+        const f3 vse = mk3((float)ex, (float)ey, (float)ez);
+        f3 ep = (vse / V.resf) * (V.bmax - V.bmin) + V.bmin;      // :90
+        ep = ep + mk3(u.y, u.z, u.w) * V.vsize;                   // :92
+        const f3 toL = ep - hb.position;                          // :94
+        const float r = length(toL);
+        const f3 w = toL / r;                                     // :96
+        Basis lb;
+        voxel_to_world(V, vse, hb.position, w, lb);               // :103-106
+        const float area = 6.0f * V.vsize.x * V.vsize.y;          // :113
+        const float jac = (r * r) / gabs(dot(-w, lb.normal));     // :114
+        wl = mk4(w, jac / area);                                  // :115
+    } else {
+        L = sample_env<COUNT>(F, hb, u.y, u.z, wl, tl);           // :120
+    }
+    wl.w = wl.w / (float)num_lights;                              // :124
+    const f3 wdir = xyz(wl);
+    f3 shadow_hit; bool hit_ground;
+    const bool missed = !traverse<COUNT>(V, hb.position, wdir, shadow_hit, hit_ground, tl);   // :133
+    if (sampling_voxel) {
+        if (missed || shadow_hit.x != (float)ex || shadow_hit.y != (float)ey || shadow_hit.z != (float)ez)
+            return mk3(0.0f);                                     // :138-142
+    } else {
+        if (!missed) return mk3(0.0f);                            // :148-152
+    }
+    const f3 lsWo = world_to_local(wo, hb);                       // :159
+    const f3 lsWi = world_to_local(wdir, hb);
+    const f4 bf = evaluate_material<COUNT>(F, mat_off, lsWo, lsWi, tl);     // :161
+    const float mis = power_heuristic(wl.w, bf.w);                // :163
+    return xyz(bf) * L * gabs(dot(wdir, hb.normal)) * mis / wl.w; // :164
+}
+
+VT_DEV f3 tonemap(f3 rad)                                         // pathTracer.fs:294 (exposure 1, gamma 2.2: :43-44)
+{
+    const float inv_gamma = 1.0f / 2.2f;
+    const f3 r = rad * 1.0f;
+    return mk3(gpow(r.x, inv_gamma), gpow(r.y, inv_gamma), gpow(r.z, inv_gamma));
+}
+
+VT_DEV float wireframe_factor(const Volume& V, const Frame& F, const Basis& hb, f3 vs_hit)   // pathTracer.fs:260-270
+{
+    const f3 ctr = ((hb.position - V.bmin) / (V.bmax - V.bmin)) * V.resf;
+    const f3 uvw = vs_hit - ctr;
+    const f3 n = hb.normal;
+    const float ux = gabs(dot(mk3(n.y, n.z, n.x), uvw));
+    const float uy = gabs(dot(mk3(n.z, n.x, n.y), uvw));
+    const float th = F.wire_thickness;
+    const float w = gstep(th, ux) * gstep(ux, 1.0f - th) * gstep(th, uy) * gstep(uy, 1.0f - th);
+    return (1.0f - F.wire_opacity) + F.wire_opacity * w;
+}
+
+VT_DEV int hit_code(const Volume& V, f3 p, bool ground)
+{
+    if (ground) return -2;
+    return f2i(p.x) + f2i(p.y) * V.X + f2i(p.z) * V.X * V.Y;
+}
+
+// pathTracer.fs:172-296 for one fragment; returns the tone-mapped sample
+template <bool COUNT>
+VT_DEV f4 trace_pixel(const Volume& V, const Frame& F, int px, int py, int sample_count, int* primary, Tally<COUNT>& tl)
+{
+    const f3 frag = mk3((float)px + 0.5f, (float)py + 0.5f, 0.55f);   // gl_FragCoord (z: quad drawn at z = near = 0.1, identity MVP)
+    int2 rng = rng_offset(px, py, sample_count, F.noise_w, F.noise_h);   // :174
+    f3 radiance = mk3(0.0f), ro, rd, hit;
+    generate_ray<COUNT>(F, frag, rng, ro, rd, tl);                // :179
+    const float t = ray_aabb(ro, rd, V.bmin, V.bmax);             // :183
+    if (primary) *primary = -1;
+    if (t < 0.0f) return mk4(tonemap(background_color<COUNT>(F, rd, tl)), 1.0f);     // :187-194
+    const f3 entry = ro + t * rd;                                 // :196
+    f3 throughput = mk3(1.0f);
+    bool hit_ground;
+    if (!traverse<COUNT>(V, entry, rd, hit, hit_ground, tl))      // :202-208
+        return mk4(tonemap(background_color<COUNT>(F, rd, tl)), 1.0f);
+    if (primary) *primary = hit_code(V, hit, hit_ground);
+
+    const int sel_x = F.shared->sel_index[0], sel_y = F.shared->sel_index[1], sel_z = F.shared->sel_index[2];
+    int bounces = 0;
+    while (bounces < F.max_bounces) {                             // :214
+        Basis hb;
+        voxel_to_world(V, hit, ro, rd, hb);                       // :221-223
+        const int ix = f2i(hit.x), iy = f2i(hit.y), iz = f2i(hit.z);   // :225
+        const int mat_off = fetch_offset(V, ix, iy, iz);          // :226
+        if (ix == sel_x && iy == sel_y && iz == sel_z) { radiance = radiance + mk3(1.0f, 0.0f, 0.0f); break; }   // :228-233
+        const f3 wo = -rd;                                        // :237
+        const f3 lsWo = world_to_local(wo, hb);
+        if (bounces == 0) radiance = radiance + throughput * emission_material<COUNT>(F, mat_off, tl);          // :241-245
+        radiance = radiance + throughput * direct_lighting<COUNT>(V, F, mat_off, hb, wo, rng, tl);              // :248
+        f4 bf;
+        const f3 lsWi = sample_material<COUNT>(F, mat_off, lsWo, rng, bf, tl);                                  // :255
+        if (F.wire_opacity > 0.0f) {                              // :260-270
+            const float w = wireframe_factor(V, F, hb, hit);
+            bf.x *= w; bf.y *= w; bf.z *= w;
+        }
+        const f3 wi = local_to_world(lsWi, hb);                   // :273
+        throughput = throughput * ((xyz(bf) * gabs(dot(wi, hb.normal))) / bf.w);                                // :276
+        ro = hb.position; rd = wi;                                // :278-279
+        if (!traverse<COUNT>(V, ro, rd, hit, hit_ground, tl)) {   // :282-289
+            const f4 Lp = evaluate_env<COUNT>(F, rd, tl);
+            const float mis = power_heuristic(bf.w, Lp.w);
+            radiance = radiance + (throughput * xyz(Lp)) * mis;
+            break;
+        }
+        bounces++;
+    }
+    return mk4(tonemap(radiance), 1.0f);                          // :294-295
+}
+
+// integrator/editMode.fs:62-142
+template <bool COUNT>
+VT_DEV f4 preview_pixel(const Volume& V, const Frame& F, int px, int py, int sample_count, int* primary, Tally<COUNT>& tl)
+{
+    const f3 frag = mk3((float)px + 0.5f, (float)py + 0.5f, 0.55f);
+    int2 rng = rng_offset(px, py, sample_count, F.noise_w, F.noise_h);
+    f3 ro, rd, hit;
+    generate_ray<COUNT>(F, frag, rng, ro, rd, tl);
+    const float t = ray_aabb(ro, rd, V.bmin, V.bmax);
+    if (primary) *primary = -1;
+    if (t < 0.0f) return mk4(background_color<COUNT>(F, rd, tl), 1.0f);
+    const f3 entry = ro + t * rd;
+    bool hit_ground;
+    if (!traverse<COUNT>(V, entry, rd, hit, hit_ground, tl)) return mk4(background_color<COUNT>(F, rd, tl), 1.0f);
+    if (primary) *primary = hit_code(V, hit, hit_ground);
+    Basis hb;
+    voxel_to_world(V, hit, ro, rd, hb);
+    if (f2i(hit.x) == F.shared->sel_index[0] && f2i(hit.y) == F.shared->sel_index[1] && f2i(hit.z) == F.shared->sel_index[2])
+        return mk4(1.0f, 0.0f, 0.0f, 1.0f);                       // :107-112
+    f3 albedo = mk3(1.0f);
+    if (F.wire_opacity > 0.0f) albedo = albedo * wireframe_factor(V, F, hb, hit);
+    float lighting = gmax(0.0f, dot(-rd, hb.normal));             // :130
+    lighting = sqrtf(lighting);
+    const f3 light_dir = mk3(1.0f, -1.0f, -1.0f);                 // :41 (never set by the host: SURVEY appendix B)
+    f3 sh; bool g2;
+    if (traverse<COUNT>(V, hb.position, -light_dir, sh, g2, tl)) lighting *= 0.5f;   // :134-137, ambientLight :42
+    return mk4(albedo * lighting, 1.0f);
+}
+
+} // namespace vt

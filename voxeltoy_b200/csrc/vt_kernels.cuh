@@ -1,0 +1,361 @@
+// vt_kernels.cuh -- __global__ kernels of the voxelToy hot path (sm_100a).
+//   K1+K2  vt_render_kernel      path trace (pathTracer.fs) or preview (editMode.fs) fused with the
+//                                running-average accumulation (accumulation.fs)
+//   K5     vt_voxelize_kernel    warp-per-triangle THIN surface voxelization (voxelize.gs), atomicOr scatter
+//   K6-K9  vt_pick_kernel / vt_pick_focal_kernel / vt_add_voxel_kernel / vt_remove_voxel_kernel
+//   layout vt_build_bricks_kernel / vt_build_supers_kernel / vt_fill_offsets_kernel
+#pragma once
+#include "vt_device.cuh"
+
+namespace vt {
+
+// tile geometry of the frame partition: 64x64 pixel tiles dealt round-robin to ranks;
+// inside a tile, CTAs of 128 threads cover 16x8 pixels as four 8x4 warps.
+constexpr int kTile = 64;
+constexpr int kCtaW = 16, kCtaH = 8;
+constexpr int kCtasPerTile = (kTile / kCtaW) * (kTile / kCtaH);   // 32
+
+struct RenderLaunch {
+    int first_sample;     // sampleCount uniform of pass 0
+    int sample_stride;    // sampleCount advance per pass (world size in sample-partition mode, else 1)
+    int n_passes;
+    int n_prev;           // passes already folded into accum (the `sampleCount` of accumulation.fs)
+    int sum_mode;         // 1: accum += sample (sample partition; divide after the cross-GPU reduce)
+    int integrator;       // 0 path tracer, 1 edit mode
+    int tiles_x, tiles_y;
+    int tile_rank, tile_world;   // this context renders tiles t with t % tile_world == tile_rank
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128)
+vt_render_kernel(const Volume V, const Frame F, const RenderLaunch L,
+                 float4* __restrict__ accum, int* __restrict__ primary, Counters* __restrict__ counters)
+{
+    // CTA -> tile -> pixel
+    const int local_tile = blockIdx.x / kCtasPerTile;
+    const int in_tile = blockIdx.x - local_tile * kCtasPerTile;
+    const int tile = L.tile_rank + local_tile * L.tile_world;
+    const int tx = tile % L.tiles_x, ty = tile / L.tiles_x;
+    const int cx = in_tile % (kTile / kCtaW), cy = in_tile / (kTile / kCtaW);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tx * kTile + cx * kCtaW + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * kTile + cy * kCtaH + (warp >> 1) * 4 + (lane >> 3);
+    const bool active = (px < F.W) && (py < F.H);
+
+    Tally<COUNT> tl; tl.clear();
+    if (active) {
+        const size_t pix = (size_t)px + (size_t)py * (size_t)F.W;
+        float4 avg = accum[pix];
+        int prim = -1;
+        for (int p = 0; p < L.n_passes; ++p) {
+            const int sample = L.first_sample + p * L.sample_stride;
+            int* pp = (primary != nullptr && p == L.n_passes - 1) ? &prim : nullptr;
+            const f4 s = (L.integrator == 0) ? trace_pixel<COUNT>(V, F, px, py, sample, pp, tl)
+                                             : preview_pixel<COUNT>(V, F, px, py, sample, pp, tl);
+            if (L.sum_mode) {
+                avg.x = avg.x + s.x; avg.y = avg.y + s.y; avg.z = avg.z + s.z; avg.w = avg.w + s.w;
+            } else {
+                // accumulation.fs:17  (sample + average * sampleCount) / (sampleCount + 1)
+                const float n = (float)(L.n_prev + p), n1 = (float)(L.n_prev + p + 1);
+                avg.x = (s.x + avg.x * n) / n1; avg.y = (s.y + avg.y * n) / n1;
+                avg.z = (s.z + avg.z * n) / n1; avg.w = (s.w + avg.w * n) / n1;
+            }
+        }
+        accum[pix] = avg;
+        if (primary != nullptr) primary[pix] = prim;
+    }
+    if (COUNT) {
+        // warp-reduce, one atomic per warp per counter
+        unsigned long long v[5] = { tl.S, tl.R, tl.H, tl.E, tl.Q };
+        #pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            unsigned long long x = v[i];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            v[i] = x;
+        }
+        if (lane == 0) {
+            atomicAdd(&counters->S, v[0]); atomicAdd(&counters->R, v[1]); atomicAdd(&counters->H, v[2]);
+            atomicAdd(&counters->E, v[3]); atomicAdd(&counters->Q, v[4]);
+        }
+    }
+}
+
+// ---- services ------------------------------------------------------------------------------
+// selectVoxel.vs:36-71. The pick ray is the un-jittered pinhole ray.
+__global__ void vt_pick_kernel(const Volume V, const Frame F, float px, float py, Shared* sh)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Tally<false> tl; tl.clear();
+    f3 ro, rd, hit; bool g;
+    pinhole_ray(F, mk3(px, py, F.near_z), 0.5f, 0.5f, ro, rd);          // :41
+    const float t = ray_aabb(ro, rd, V.bmin, V.bmax);
+    sh->sel_index[0] = sh->sel_index[1] = sh->sel_index[2] = sh->sel_index[3] = 0;   // :47
+    if (t < 0.0f) return;
+    const f3 p = ro + t * rd;
+    if (!traverse<false>(V, p, rd, hit, g, tl)) return;
+    Basis hb;
+    voxel_to_world(V, hit, ro, rd, hb);
+    sh->sel_index[0] = f2i(hit.x); sh->sel_index[1] = f2i(hit.y); sh->sel_index[2] = f2i(hit.z); sh->sel_index[3] = 0;   // :69
+    sh->sel_normal[0] = hb.normal.x; sh->sel_normal[1] = hb.normal.y; sh->sel_normal[2] = hb.normal.z; sh->sel_normal[3] = 0.0f;
+}
+
+// focalDistance.vs:45-81
+__global__ void vt_pick_focal_kernel(const Volume V, const Frame F, float px, float py, Shared* sh)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Tally<false> tl; tl.clear();
+    f3 ro, rd, hit; bool g;
+    pinhole_ray(F, mk3(px, py, 0.0f), 0.5f, 0.5f, ro, rd);               // :51
+    const float t = ray_aabb(ro, rd, V.bmin, V.bmax);
+    sh->focal_distance = 99999999.0f;                                    // :43,57
+    if (t < 0.0f) return;
+    const f3 p = ro + t * rd;
+    if (!traverse<false>(V, p, rd, hit, g, tl)) return;
+    const f3 vmin = hit * V.vsize + V.bmin;                              // :76-78
+    const f3 vmax = vmin + V.vsize;
+    sh->focal_distance = ray_aabb(ro, rd, vmin, vmax);
+}
+
+VT_DEV void set_voxel_bits(unsigned long long* bricks, unsigned long long* supers, const Volume& V, int x, int y, int z, bool on)
+{
+    const int bx = x >> 2, by = y >> 2, bz = z >> 2;
+    const int key = bx + by * V.BX + bz * V.BXY;
+    const unsigned long long bit = 1ull << ((x & 3) | ((y & 3) << 2) | ((z & 3) << 4));
+    unsigned long long b = bricks[key];
+    b = on ? (b | bit) : (b & ~bit);
+    bricks[key] = b;
+    const int sk = (bx >> 2) + (by >> 2) * V.SX + (bz >> 2) * V.SXY;
+    const unsigned long long sbit = 1ull << ((bx & 3) | ((by & 3) << 2) | ((bz & 3) << 4));
+    unsigned long long s = supers[sk];
+    s = (b != 0ull) ? (s | sbit) : (s & ~sbit);
+    supers[sk] = s;
+}
+
+// addVoxel.vs:16-41. result[0] = 1 if a voxel was written, result[1..3] = its coordinate.
+__global__ void vt_add_voxel_kernel(const Volume V, const Frame F, float mx, float my, const Shared* sh,
+                                    int* mat, unsigned long long* bricks, unsigned long long* supers, int* result)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const f3 right = xyz(mul44(F.inv_mv, 1.0f, 0.0f, 0.0f, 0.0f));     // :18
+    const f3 up = xyz(mul44(F.inv_mv, 0.0f, 1.0f, 0.0f, 0.0f));        // :19
+    const f3 ar = gabs(right), au = gabs(up);
+    const f3 aar = (mk3(gstep(ar.y, ar.x), gstep(ar.x, ar.y), gstep(ar.x, ar.z)) *
+                    mk3(gstep(ar.z, ar.x), gstep(ar.z, ar.y), gstep(ar.y, ar.z))) * gsign(right);   // :24
+    const f3 aau = (mk3(gstep(au.y, au.x), gstep(au.x, au.y), gstep(au.x, au.z)) *
+                    mk3(gstep(au.z, au.x), gstep(au.z, au.y), gstep(au.y, au.z))) * gsign(up);      // :25
+    const float amx = gabs(mx), amy = gabs(my);
+    const float kx = gstep(amy, amx) * gsign(mx);                       // :28-29
+    const float ky = gstep(amx, amy) * gsign(my);
+    f3 normal;
+    if (amx != 0.0f || amy != 0.0f) normal = aar * kx + aau * ky;       // :30-32
+    else normal = mk3(sh->sel_normal[0], sh->sel_normal[1], sh->sel_normal[2]);
+    const int cx = sh->sel_index[0] + f2i(normal.x);                   // :35
+    const int cy = sh->sel_index[1] + f2i(normal.y);
+    const int cz = sh->sel_index[2] + f2i(normal.z);
+    result[0] = 0; result[1] = cx; result[2] = cy; result[3] = cz;
+    if ((unsigned)cx >= (unsigned)V.X || (unsigned)cy >= (unsigned)V.Y || (unsigned)cz >= (unsigned)V.Z) return;
+    int off = fetch_offset(V, sh->sel_index[0], sh->sel_index[1], sh->sel_index[2]);   // :37-40 (material of the selected voxel)
+    if (off < 0) off = 0;
+    mat[(size_t)cx + (size_t)cy * V.X + (size_t)cz * V.X * V.Y] = off;
+    set_voxel_bits(bricks, supers, V, cx, cy, cz, true);
+    result[0] = 1;
+}
+
+// removeVoxel.vs:8-11 (contract N2: the voxel becomes empty)
+__global__ void vt_remove_voxel_kernel(const Volume V, const Shared* sh,
+                                       int* mat, unsigned long long* bricks, unsigned long long* supers, int* result)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int x = sh->sel_index[0], y = sh->sel_index[1], z = sh->sel_index[2];
+    result[0] = 0; result[1] = x; result[2] = y; result[3] = z;
+    if ((unsigned)x >= (unsigned)V.X || (unsigned)y >= (unsigned)V.Y || (unsigned)z >= (unsigned)V.Z) return;
+    mat[(size_t)x + (size_t)y * V.X + (size_t)z * V.X * V.Y] = -1;
+    set_voxel_bits(bricks, supers, V, x, y, z, false);
+    result[0] = 1;
+}
+
+// ---- occupancy layout ------------------------------------------------------------------------
+// one thread per (brick, z-slice-of-4): builds 16 bits; a 4-thread group ORs them with shuffles.
+// Simpler and fast enough (upload-time only): one thread per brick row (4 voxels in x) -> atomicOr.
+__global__ void vt_build_bricks_kernel(const int* __restrict__ mat, unsigned long long* __restrict__ bricks,
+                                       int X, int Y, int Z, int BX, int BXY)
+{
+    // thread -> (bx, y, z): reads up to 4 consecutive ints
+    const size_t n = (size_t)BX * (size_t)Y * (size_t)Z;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int bx = (int)(i % BX);
+        const size_t r = i / BX;
+        const int y = (int)(r % Y), z = (int)(r / Y);
+        const int x0 = bx << 2;
+        const int* row = mat + ((size_t)x0 + (size_t)y * X + (size_t)z * X * Y);
+        unsigned int m = 0;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x0 + k < X && __ldg(row + k) >= 0) m |= 1u << k;
+        if (m) {
+            const int sh = ((y & 3) << 2) | ((z & 3) << 4);
+            atomicOr(bricks + ((size_t)bx + (size_t)(y >> 2) * BX + (size_t)(z >> 2) * BXY), (unsigned long long)m << sh);
+        }
+    }
+}
+
+__global__ void vt_build_supers_kernel(const unsigned long long* __restrict__ bricks, unsigned long long* __restrict__ supers,
+                                       int BX, int BY, int BZ, int SX, int SXY)
+{
+    const size_t n = (size_t)BX * BY * BZ;
+    const int BXY = BX * BY;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (__ldg(bricks + i) == 0ull) continue;
+        const int bz = (int)(i / BXY);
+        const int r = (int)(i - (size_t)bz * BXY);
+        const int by = r / BX, bx = r - by * BX;
+        const int sbit = (bx & 3) | ((by & 3) << 2) | ((bz & 3) << 4);
+        atomicOr(supers + ((size_t)(bx >> 2) + (size_t)(by >> 2) * SX + (size_t)(bz >> 2) * SXY), 1ull << sbit);
+    }
+}
+
+// material-offset grid from occupancy: voxel = bit ? fill : -1. One thread per x-run of 4 voxels.
+__global__ void vt_fill_offsets_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
+                                       int X, int Y, int Z, int BX, int BXY, int fill)
+{
+    const size_t n = (size_t)BX * (size_t)Y * (size_t)Z;
+    const bool vec = (X & 3) == 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int bx = (int)(i % BX);
+        const size_t r = i / BX;
+        const int y = (int)(r % Y), z = (int)(r / Y);
+        const unsigned long long b = __ldg(bricks + ((size_t)bx + (size_t)(y >> 2) * BX + (size_t)(z >> 2) * BXY));
+        const unsigned int m = (unsigned int)(b >> (((y & 3) << 2) | ((z & 3) << 4))) & 0xfu;
+        int* row = mat + ((size_t)(bx << 2) + (size_t)y * X + (size_t)z * X * Y);
+        if (vec) {
+            int4 v;
+            v.x = (m & 1u) ? fill : -1; v.y = (m & 2u) ? fill : -1; v.z = (m & 4u) ? fill : -1; v.w = (m & 8u) ? fill : -1;
+            *reinterpret_cast<int4*>(row) = v;
+        } else {
+            for (int k = 0; k < 4; ++k) if ((bx << 2) + k < X) row[k] = ((m >> k) & 1u) ? fill : -1;
+        }
+    }
+}
+
+// ---- voxelizer --------------------------------------------------------------------------------
+// voxelize.vs:20-28 + voxelize.gs:55-251 (THIN). One warp per triangle; lanes stride over the (x,y)
+// columns of the swizzled bounding box, each column resolves its short z-range. The set of voxels
+// written is order independent, so atomicOr into the bit-packed bricks reproduces the reference's
+// imageStore scatter exactly.
+VT_DEV f2 edge_n(float nc, float ea, float eb) { return (nc >= 0.0f) ? mk2(-eb, ea) : mk2(eb, -ea); }
+VT_DEV float edge_d(f2 n, float va, float vb)                      // voxelize.gs:140
+{
+    return dot(n, mk2(0.5f - va, 0.5f - vb)) + 0.5f * gmax(gabs(n.x), gabs(n.y));
+}
+
+__global__ void __launch_bounds__(128)
+vt_voxelize_kernel(const float* __restrict__ xyz_in, const unsigned int* __restrict__ idx, int n_tris,
+                   const float* __restrict__ M, int X, int Y, int Z, int BX, int BXY,
+                   unsigned long long* __restrict__ bricks)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps_per_cta = blockDim.x >> 5;
+    float m[16];
+    #pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = __ldg(M + i);
+    for (int tri = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); tri < n_tris; tri += gridDim.x * warps_per_cta) {
+        f3 v[3];
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const unsigned int vi = __ldg(idx + 3 * (size_t)tri + k);
+            const float x = __ldg(xyz_in + 3 * (size_t)vi), y = __ldg(xyz_in + 3 * (size_t)vi + 1), z = __ldg(xyz_in + 3 * (size_t)vi + 2);
+            const f4 l = mul44(m, x, y, z, 1.0f);                  // voxelize.vs:23
+            v[k] = mk3(l.x * (float)X, l.y * (float)Y, l.z * (float)Z);   // :25
+        }
+        f3 v0 = v[0], v1 = v[1], v2 = v[2];
+        // swizzleTri, voxelize.gs:55-109
+        f3 n = cross(v1 - v0, v2 - v1);
+        const f3 an = gabs(n);
+        int axis;
+        if (an.x >= an.y && an.x >= an.z) {
+            axis = 0;
+            v0 = mk3(v0.y, v0.z, v0.x); v1 = mk3(v1.y, v1.z, v1.x); v2 = mk3(v2.y, v2.z, v2.x); n = mk3(n.y, n.z, n.x);
+        } else if (an.y >= an.x && an.y >= an.z) {
+            axis = 1;
+            v0 = mk3(v0.z, v0.x, v0.y); v1 = mk3(v1.z, v1.x, v1.y); v2 = mk3(v2.z, v2.x, v2.y); n = mk3(n.z, n.x, n.y);
+        } else axis = 2;
+        // main, voxelize.gs:244-248 (clamps against the un-permuted resolution)
+        const f3 mn = gmin(gmin(v0, v1), v2), mx = gmax(gmax(v0, v1), v2);
+        const int lox = f2i(gclamp(floorf(mn.x), 0.0f, (float)X)), hix = f2i(gclamp(ceilf(mx.x), 0.0f, (float)X));
+        const int loy = f2i(gclamp(floorf(mn.y), 0.0f, (float)Y)), hiy = f2i(gclamp(ceilf(mx.y), 0.0f, (float)Y));
+        const int loz = f2i(gclamp(floorf(mn.z), 0.0f, (float)Z)), hiz = f2i(gclamp(ceilf(mx.z), 0.0f, (float)Z));
+        // voxelizeTriPostSwizzle, voxelize.gs:118-232
+        const f3 e0 = v1 - v0, e1 = v2 - v1, e2 = v0 - v2;
+        const f2 n0xy = edge_n(n.z, e0.x, e0.y), n1xy = edge_n(n.z, e1.x, e1.y), n2xy = edge_n(n.z, e2.x, e2.y);
+        const f2 n0yz = edge_n(n.x, e0.y, e0.z), n1yz = edge_n(n.x, e1.y, e1.z), n2yz = edge_n(n.x, e2.y, e2.z);
+        const f2 n0zx = edge_n(n.y, e0.z, e0.x), n1zx = edge_n(n.y, e1.z, e1.x), n2zx = edge_n(n.y, e2.z, e2.x);
+        const float d0xy = edge_d(n0xy, v0.x, v0.y), d1xy = edge_d(n1xy, v1.x, v1.y), d2xy = edge_d(n2xy, v2.x, v2.y);
+        const float d0yz = edge_d(n0yz, v0.y, v0.z), d1yz = edge_d(n1yz, v1.y, v1.z), d2yz = edge_d(n2yz, v2.y, v2.z);
+        const float d0zx = edge_d(n0zx, v0.z, v0.x), d1zx = edge_d(n1zx, v1.z, v1.x), d2zx = edge_d(n2zx, v2.z, v2.x);
+        const f3 nP = (n.z < 0.0f) ? -n : n;
+        const float dTri = dot(nP, v0);
+        const float dThin = dTri - dot(mk2(nP.x, nP.y), mk2(0.5f, 0.5f));
+        const float nzInv = 1.0f / nP.z;
+
+        const int wx = hix - lox, wy = hiy - loy;
+        const long long ncols = (wx > 0 && wy > 0) ? (long long)wx * wy : 0;
+        for (long long c = lane; c < ncols; c += 32) {
+            const int px = lox + (int)(c / wy), py = loy + (int)(c % wy);   // y fastest, like the reference's loop nest
+            const f2 pxy = mk2((float)px, (float)py);
+            const float a0 = d0xy + dot(n0xy, pxy), a1 = d1xy + dot(n1xy, pxy), a2 = d2xy + dot(n2xy, pxy);
+            if (!((a0 >= 0.0f) && (a1 >= 0.0f) && (a2 >= 0.0f))) continue;
+            const float dot_n_p = dot(mk2(nP.x, nP.y), pxy);
+            const float zInt = (-dot_n_p + dThin) * nzInv;
+            const float zf = floorf(zInt), zc = ceilf(zInt);
+            int zMin = f2i(zf) - ((zf == zInt) ? 1 : 0);
+            int zMax = f2i(zc) + ((zc == zInt) ? 1 : 0);
+            zMin = max(loz, zMin); zMax = min(hiz, zMax);
+            for (int pz = zMin; pz < zMax; ++pz) {
+                const f2 pyz = mk2((float)py, (float)pz), pzx = mk2((float)pz, (float)px);
+                const float b0 = d0yz + dot(n0yz, pyz), b1 = d1yz + dot(n1yz, pyz), b2 = d2yz + dot(n2yz, pyz);
+                const float c0 = d0zx + dot(n0zx, pzx), c1 = d1zx + dot(n1zx, pzx), c2 = d2zx + dot(n2zx, pzx);
+                if ((b0 >= 0.0f) && (b1 >= 0.0f) && (b2 >= 0.0f) && (c0 >= 0.0f) && (c1 >= 0.0f) && (c2 >= 0.0f)) {
+                    int ox, oy, oz;                                   // unswizzle, voxelize.gs:40-48
+                    if (axis == 0) { ox = pz; oy = px; oz = py; }
+                    else if (axis == 1) { ox = py; oy = pz; oz = px; }
+                    else { ox = px; oy = py; oz = pz; }
+                    if ((unsigned)ox < (unsigned)X && (unsigned)oy < (unsigned)Y && (unsigned)oz < (unsigned)Z) {
+                        const int key = (ox >> 2) + (oy >> 2) * BX + (oz >> 2) * BXY;
+                        atomicOr(bricks + key, 1ull << ((ox & 3) | ((oy & 3) << 2) | ((oz & 3) << 4)));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// rule-based material assignment for solid voxels (BASELINE config 3):
+// rule 1: id = ((x>>5) ^ (y>>5) ^ (z>>5)) % n_table
+__global__ void vt_assign_materials_kernel(int* __restrict__ mat, int X, int Y, int Z,
+                                           const int* __restrict__ table, int n_table, int rule)
+{
+    const size_t n = (size_t)X * Y * Z;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (mat[i] < 0) continue;
+        const int x = (int)(i % X); const size_t r = i / X; const int y = (int)(r % Y), z = (int)(r / Y);
+        int id = 0;
+        if (rule == 1) id = ((x >> 5) ^ (y >> 5) ^ (z >> 5)) % n_table;
+        mat[i] = __ldg(table + id);
+    }
+}
+
+// test hook: the DDA alone
+__global__ void vt_trace_rays_kernel(const Volume V, const float* __restrict__ rays, size_t n, float* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Tally<false> tl; tl.clear();
+    const f3 o = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
+    const f3 d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+    f3 hit; bool g;
+    const bool h = traverse<false>(V, o, d, hit, g, tl);
+    out[4 * i] = hit.x; out[4 * i + 1] = hit.y; out[4 * i + 2] = hit.z;
+    out[4 * i + 3] = h ? (g ? 2.0f : 1.0f) : 0.0f;
+}
+
+} // namespace vt
