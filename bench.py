@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of voxeltoy_b200 (contract: see the task statement / DESIGN.md "Measurement").
+
+Metric (BASELINE.json): path-traced Msamples/s @1080p, 4 bounces. Workload at every N: BASELINE config 2,
+`resources/scene_fall.vox` at 1920x1080, 4 bounces, importance-sampled IBL + thin-lens DOF (synthetic HDR
+environment). One STEP = one batch of PASSES progressive passes over the whole frame through
+vt_render (path trace fused with the running accumulation). With N GPUs the samples are partitioned
+(rank r renders sampleCount = p*N + r): per-GPU work is fixed (weak scaling) and each step ends
+with an NCCL reduce of the float4 accumulators to rank 0 inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, BOUNCES, PASSES = 1920, 1080, 4, 8
+THETA, PHI, FSTOP = 120.0, 30.0, 2.8
+WORKLOAD = "C2: scene_fall.vox 1920x1080, 4 bounces, IBL + thin-lens DOF, %d passes/step" % PASSES
+
+
+# ---------------------------------------------------------------------------------------------------
+# scene set-up through the product's host classes (the reference's Renderer API; no oracle code on this path)
+# ---------------------------------------------------------------------------------------------------
+def setup_renderer(device):
+    """Config 2 driven the way the reference's UI drives its Renderer."""
+    import tempfile
+    from voxeltoy_b200 import host, scenes
+    r = host.Renderer()
+    r.initialize("", device)
+    r.resizeFrame(W, H)
+    r.loadVoxFile(os.path.join(ROOT, "tests", "golden", "scene_fall.vox.gz"))
+    env_path = os.path.join(tempfile.gettempdir(), "voxeltoy_b200_c2_env_%d.pfm" % os.getpid())
+    host.write_pfm(env_path, scenes.synthetic_env(1024, 512))
+    r.setRenderSettings(maxBounces=BOUNCES, backgroundImage=env_path)
+    cam = r.camera()
+    cam.setLensModel(host.CLM_THIN_LENS)
+    cam.controller().orbitAroundTarget(np.radians(THETA), np.radians(PHI))
+    cam.setFStop(FSTOP)
+    ctx = r.context()
+    ctx.set_selection([-1, -1, -1, 0], [1, 0, 0, 0])                   # no highlighted voxel
+    r.requestAction(0.5, 0.5, 0.0, 0.0, host.PA_SELECT_FOCAL_POINT)    # autofocus on the image centre, runs before the next pass
+    r.renderPasses(1)
+    r.resetRender()
+    return r, ctx
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def bytes_per_sample(c, n_samples):
+    """4S + 16R + 36H + 4E + 64Q + 32 algorithmic bytes per sample."""
+    return (4 * c["dda_steps"] + 16 * c["rand_calls"] + 36 * c["material_evals"] + 4 * c["cdf_loads"]
+            + 64 * c["env_lookups"]) / float(n_samples) + 32.0
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, sample_rows=None):
+    """The CPU arm: the reference's shaders compiled for the host (oracle/_ref) when present, else the C oracle port,
+    on all host cores, over a bounded sample of the SAME workload (full-width rows of the C2 frame, 1 pass)."""
+    from oracle import refrun
+    return refrun.time_c2(W, H, BOUNCES, THETA, PHI, FSTOP, steps=steps, warmup=warmup, rows=sample_rows)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(3, args.warmup)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference_run(max(1, args.steps), max(1, args.warmup))
+        line = {"impl": "reference", "metric": "path-traced Msamples/s @1080p, 4 bounces", "value": r["value"], "unit": "Msamples/s",
+                "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "sample": r["sample"]},
+                "cpu_baseline": {"value": r["value"], "unit": "Msamples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import voxeltoy_b200 as vt
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- voxeltoy_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    r, ctx = setup_renderer(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        r.setPartition(vt.VT_PART_SAMPLES, rank, world)
+    vol = vt.host.load_vox(os.path.join(ROOT, "tests", "golden", "scene_fall.vox.gz"))     # host arrays for the e2e leg
+
+    npx = W * H
+    accum = vt.host.device_view(ctx.accum_device_ptr(), (H, W, 4))          # zero-copy torch view of the accumulator
+    reduce_buf = torch.empty_like(accum) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
+    pinned_out = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
+
+    def reduce_step():
+        if world > 1:
+            reduce_buf.copy_(accum)
+            dist.reduce(reduce_buf, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        r.renderPasses(PASSES)
+        reduce_step()
+    barrier()
+    r.resetRender()
+    launches0 = ctx.counters()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)                                              # L2 flush between timed iterations (untimed)
+        e0, e1 = evs[i]
+        k0, k1 = kevs[i]
+        e0.record(stream)
+        k0.record(stream)
+        r.renderPasses(PASSES)                                             # progressive: continues the running average
+        k1.record(stream)
+        reduce_step()
+        e1.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.counters()["kernel_launches"] - launches0
+    ms_steps = sum(a.elapsed_time(b) for a, b in evs)
+    ms_kernel = sum(a.elapsed_time(b) for a, b in kevs) / args.steps
+    t = torch.tensor([ms_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    samples_total = float(npx) * PASSES * args.steps * world
+    value = samples_total / (ms_total * 1e-3) / 1e6
+
+    # ---- end to end through the host-facing API: every step hands the scene arrays to the Renderer from host memory
+    # (setVoxelData = createVoxelDataTexture: H2D of grid + materials, occupancy rebuild), renders PASSES passes and reads
+    # the frame back into pinned host memory.
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = vol["grid"].nbytes + vol["materials"].nbytes + vol["emissive"].nbytes + 3 * 64 + 64
+    d2h = npx * 16
+    barrier()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record(stream)
+    for i in range(e2e_steps):
+        r.setVoxelData(vol["res"], vol["grid"], vol["materials"], vol["emissive"])
+        cam = r.camera(); cam.controller().orbitAroundTarget(np.radians(THETA), np.radians(PHI))
+        r.renderPasses(PASSES)
+        if world > 1:
+            reduce_step()
+            pinned_out.copy_(reduce_buf, non_blocking=True)
+            stream.synchronize()
+        else:
+            r.readAverage(pinned_out)
+        _ = float(pinned_out[H // 2, W // 2, 0])
+    ee1.record(stream)
+    barrier()
+    te = torch.tensor([ee0.elapsed_time(ee1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = float(npx) * PASSES * e2e_steps * world / (float(te.item()) * 1e-3) / 1e6
+
+    # ---- algorithmic bytes of the timed launches (counted replay, untimed): same sample indices => identical work
+    r.resetRender()
+    ctx.counters_enable(True); ctx.reset_counters()
+    n_count = min(args.steps, 4)
+    for i in range(n_count):
+        r.renderPasses(PASSES)
+    ctx.sync()
+    cnt = ctx.counters(); ctx.counters_enable(False)
+    bps = bytes_per_sample(cnt, npx * PASSES * n_count)
+    bytes_per_launch = bps * npx * PASSES
+    achieved = bytes_per_launch / (ms_kernel * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("vt_render_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    if rank == 0:
+        line = {
+            "metric": "path-traced Msamples/s @1080p, 4 bounces", "value": value, "unit": "Msamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "width": W, "height": H, "bounces": BOUNCES, "passes_per_step": PASSES,
+                       "lens": "thin f/2.8", "env": "synthetic HDR 1024x512 + CDF 512x256", "partition": "samples" if world > 1 else "none",
+                       "l2": "flushed between timed steps (256 MiB fill)", "wall_s": t_wall},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "vt_render_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_sample": bps, "ms_per_launch": ms_kernel,
+                         "per_sample": {"S": cnt["dda_steps"] / (npx * PASSES * n_count), "R": cnt["rand_calls"] / (npx * PASSES * n_count),
+                                        "H": cnt["material_evals"] / (npx * PASSES * n_count), "E": cnt["cdf_loads"] / (npx * PASSES * n_count),
+                                        "Q": cnt["env_lookups"] / (npx * PASSES * n_count)}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                r = cpu_reference_run(steps=2, warmup=1)
+                line["cpu_baseline"] = {"value": r["value"], "unit": "Msamples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            except Exception as e:   # the CPU arm is a reported baseline, never a reason to lose the GPU line
+                line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

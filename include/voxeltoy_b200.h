@@ -132,7 +132,8 @@ int vt_get_num_samples(vt_ctx* ctx, int* n);                /* m_numberSamples *
 int vt_read_average(vt_ctx* ctx, float* rgba_out);          /* glGetTexImage(average), renderer.cpp:1119-1127 */
 int vt_read_primary_hits(vt_ctx* ctx, int32_t* out);        /* per pixel: linear voxel index, -1 miss, -2 ground (last pass) */
 int vt_enable_primary_hits(vt_ctx* ctx, int enable);
-/* multi-GPU: restrict this context to its share of the frame (tiles) or of the samples. */
+/* multi-GPU: restrict this context to its share of the frame (tiles: 64x64 tiles dealt round-robin, result bit-identical
+ * to one GPU) or of the samples (rank r of `world` renders sampleCount = (first_sample + p) * world + r and keeps a SUM). */
 int vt_set_partition(vt_ctx* ctx, int mode, int rank, int world);
 /* sample-partition mode keeps a running SUM instead of an average; expose the device buffer so the caller's
  * collective (NCCL through torch.distributed) can reduce it in place. W*H float4. */

@@ -224,9 +224,10 @@ def voxelize(verts, idx, M, res, n_threads=None):
     return occ
 
 
-def pick(scene, px, py, near_z=0.1):
+def pick(scene, px, py, near_z=0.1, prev_normal=(1.0, 0.0, 0.0, 0.0)):
+    """selectVoxel.vs: index is reset to 0 on a miss, normal keeps the SSBO's previous value (:47-62)."""
     vp = np.array([0, 0, scene.W, scene.H], np.float32)
-    index = np.zeros(4, np.int32); normal = np.zeros(4, np.float32)
+    index = np.zeros(4, np.int32); normal = np.array(prev_normal, np.float32)
     lib().vto_pick(C.byref(scene), _fp(vp), near_z, px, py, _ip(index), _fp(normal))
     return index, normal
 

@@ -154,11 +154,12 @@ def test_services_pick_add_remove(vt_ctx):
     util.upload(vt_ctx, d)
     grid = vol["grid"].copy()
     rng = np.random.RandomState(4)
+    rn = np.array([1, 0, 0, 0], np.float32)
     for i in range(24):
         px, py = float(rng.uniform(0, 320)), float(rng.uniform(0, 240))
         vt_ctx.pick(px, py)
         gi, gn = vt_ctx.get_selection()
-        ri, rn = vto.pick(s, px, py, near_z=d["near_z"])
+        ri, rn = vto.pick(s, px, py, near_z=d["near_z"], prev_normal=rn)
         assert np.array_equal(gi, ri) and np.array_equal(gn, rn), (px, py, gi, ri, gn, rn)
         vt_ctx.pick_focal(px, py)
         assert vt_ctx.get_focal_distance() == vto.pick_focal(s, px, py)

@@ -1,0 +1,142 @@
+"""GPU tests of the drop-in class API: the C++ Renderer (driven through its flat wrappers the way the reference's
+UI drives it) against the CPU oracle fed with the oracle's own loaders and camera."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import scene as oscene
+from oracle import vto
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def renderer():
+    import voxeltoy_b200 as vt
+    r = vt.host.Renderer()
+    r.initialize("", 0)
+    yield r
+    r.close()
+
+
+def _oracle_frame(r, vol, bounces, env=None, lens_model=0, focal=99999999.0, sel=(0, 0, 0)):
+    imv, pm, ipm = r.cameraMatrices()
+    cp = r.camera().parameters()
+    d = dict(vol)
+    d.update(W=r.width, H=r.height, inv_modelview=imv, proj=pm, inv_proj=ipm, max_bounces=bounces, lens_model=lens_model,
+             lens_radius=cp["lensRadius"], focal_distance=focal, near_z=cp["near"], sel_index=sel,
+             bg_top=util.GRADIENT_TOP, bg_bottom=util.GRADIENT_BOTTOM)
+    if env is not None:
+        d["env"] = env
+    return d
+
+
+def test_renderer_defaults_and_load_vox(renderer):
+    """Renderer ctor + loadVoxFile defaults (renderer.cpp:41-65, import.cpp:11-44): 512x512, 1 bounce, pinhole, f/16,
+    eye at half the bounds diagonal; the default selection (0,0,0) paints that voxel red."""
+    r = renderer
+    r.loadVoxFile(util.SCENE_FALL)
+    res, bmin, bmax = r.volumeInfo()
+    assert res == (126, 20, 126)
+    cp = r.camera().parameters()
+    assert np.allclose(cp["eye"], [0, 0, -711.5], atol=0.1) and abs(cp["lensRadius"] - 1.5625) < 1e-5
+    # the host camera agrees with the oracle's independent restatement to float rounding
+    _, imv, pm, ipm = util.camera_for(res, 512, 512)
+    got = r.cameraMatrices()
+    assert np.allclose(got[0], imv, atol=1e-4) and np.allclose(got[1], pm, rtol=1e-6) and np.allclose(got[2], ipm, rtol=1e-5, atol=1e-7)
+    assert r.render() == 0 and r.numberSamples() == 1
+    r.renderPasses(2)
+    got = r.readAverage()
+    s = vto.make_scene(_oracle_frame(r, util.scene_fall_volume(), 1))
+    assert util.same_bits(got, vto.render_average(s, 3)).all()
+
+
+def test_renderer_c2_flow_env_thin_lens_autofocus(renderer, tmp_path):
+    """BASELINE config 2 at reduced size, set up exactly like bench.py does."""
+    import voxeltoy_b200 as vt
+    from voxeltoy_b200 import scenes
+    r = renderer
+    r.resizeFrame(240, 136)
+    r.loadVoxFile(util.SCENE_FALL)
+    env_rgb = scenes.synthetic_env(256, 128)
+    path = str(tmp_path / "env.pfm")
+    vt.host.write_pfm(path, env_rgb)
+    r.setRenderSettings(maxBounces=4, backgroundImage=path)
+    cam = r.camera()
+    cam.setLensModel(vt.host.CLM_THIN_LENS)
+    cam.controller().orbitAroundTarget(np.radians(120), np.radians(30))
+    cam.setFStop(2.8)
+    ctx = r.context()
+    ctx.set_selection([-1, -1, -1, 0], [1, 0, 0, 0])
+    r.requestAction(0.5, 0.5, 0, 0, vt.host.PA_SELECT_FOCAL_POINT)
+    r.renderPasses(3)
+    assert r.numberSamples() == 3
+    got = r.readAverage()
+    focal = ctx.get_focal_distance()
+    env = oscene.build_env(env_rgb)
+    d = _oracle_frame(r, util.scene_fall_volume(), 4, env=env, lens_model=1, sel=(-1, -1, -1))
+    s = vto.make_scene(d)
+    assert focal == vto.pick_focal(s, 0.5 * 240, (1.0 - 0.5) * 136)        # actions.cpp:31 flips y
+    d["focal_distance"] = focal
+    s = vto.make_scene(d)
+    assert util.same_bits(got, vto.render_average(s, 3)).all()
+    # saveImage flips vertically (renderer.cpp:1132-1136); PFM stores bottom-up, so the file equals GL order
+    out = str(tmp_path / "o.pfm")
+    r.saveImage(out)
+    assert np.array_equal(vt.host.load_image(out)[::-1], got[..., :3])
+
+
+def test_renderer_mesh_tools_and_edit_flow(renderer):
+    """loadMesh (64^3, import.cpp:75) + the add/remove tool + accumulation restart (actions.cpp:25-29)."""
+    import voxeltoy_b200 as vt
+    r = renderer
+    r.resizeFrame(160, 120)
+    r.loadMesh(util.BUNNY)
+    res, _, _ = r.volumeInfo()
+    assert res == (64, 64, 64)
+    verts, idx = oscene.load_obj(util.BUNNY)
+    bmin, bmax = oscene.mesh_bounds(verts)
+    occ = vto.voxelize(verts, idx, oscene.mesh_transform(bmin, bmax, (64, 64, 64)), (64, 64, 64))
+    ctx = r.context()
+    grid = ctx.read_volume()
+    assert np.array_equal(grid >= 0, occ > 0)
+    assert r.getMaterials() == [(0, 0)]
+    r.renderPasses(4)
+    assert r.numberSamples() == 4
+    tool = vt.host.Tool(r, 0)
+    tool.mouseMoveEvent(80, 60, 0, 0, 160, 120)                       # select under the cursor
+    tool.mousePressEvent(80, 60, vt.host.LeftButton, 0, 160, 120)     # add on the picked face
+    r.render()
+    assert r.numberSamples() == 1                                     # the actions restarted the accumulation
+    sel, normal = ctx.get_selection()
+    grid2 = ctx.read_volume()
+    changed = np.nonzero(grid2 != grid)[0]
+    assert changed.size == 1
+    c = sel[:3] + normal[:3].astype(np.int32)
+    assert changed[0] == c[0] + c[1] * 64 + c[2] * 64 * 64
+    tool.mouseMoveEvent(80, 60, vt.host.LeftButton, vt.host.ControlModifier, 160, 120)   # select + remove
+    r.render()
+    grid3 = ctx.read_volume()
+    assert (grid3 >= 0).sum() == (grid2 >= 0).sum() - 1
+    # material edit round trip (updateMaterialColor, renderer.cpp:1205-1219)
+    r.updateMaterialColor(4, [0.9, 0.1, 0.2])
+    assert np.allclose(ctx.read_materials(7)[4:7], [0.9, 0.1, 0.2])
+    # keyboard: space toggles the integrator, F focuses the bounds; both restart accumulation (renderer.cpp:670-692)
+    r.renderPasses(2)
+    assert r.onKeyPress(vt.host.Key_Space) and r.numberSamples() == 0
+    r.render()
+    assert r.onKeyPress(vt.host.Key_F) and r.numberSamples() == 0
+    assert r.onMouseMove(10, 5, vt.host.RightButton)
+    assert not r.onKeyPress(0x51)
+
+
+def test_uninitialized_renderer_is_inert():
+    import voxeltoy_b200 as vt
+    r = vt.host.Renderer()
+    assert r.render() == vt.host.RR_FINISHED_RENDERING      # renderer.cpp:558
+    r.loadVoxFile(util.SCENE_FALL)
+    r.resetRender()
+    assert r.numberSamples() == 0
+    r.close()

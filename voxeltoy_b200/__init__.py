@@ -8,4 +8,6 @@ from ._capi import (Context, VtError, load, LIB_PATH, SIGNATURES,  # noqa: F401
                     VT_INTEGRATOR_PATHTRACER, VT_INTEGRATOR_EDIT_MODE,
                     VT_PART_NONE, VT_PART_TILES, VT_PART_SAMPLES)
 
+from . import host, scenes  # noqa: E402,F401
+
 __version__ = "0.1"

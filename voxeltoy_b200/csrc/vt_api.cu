@@ -451,7 +451,8 @@ int vt_render(vt_ctx* c, int first_sample, int n_passes)
     L.tiles_x = (W + kTile - 1) / kTile; L.tiles_y = (H + kTile - 1) / kTile;
     L.tile_rank = 0; L.tile_world = 1; L.sum_mode = 0; L.first_sample = first_sample; L.sample_stride = 1;
     if (c->part_mode == VT_PART_TILES) { L.tile_rank = c->part_rank; L.tile_world = c->part_world; }
-    if (c->part_mode == VT_PART_SAMPLES) { L.sum_mode = 1; L.first_sample = first_sample + c->part_rank; L.sample_stride = c->part_world; }
+    // sample partition: first_sample counts this rank's passes; global sampleCount = (first + p) * world + rank
+    if (c->part_mode == VT_PART_SAMPLES) { L.sum_mode = 1; L.first_sample = first_sample * c->part_world + c->part_rank; L.sample_stride = c->part_world; }
     const int tiles = L.tiles_x * L.tiles_y;
     const int my_tiles = (tiles - L.tile_rank + L.tile_world - 1) / L.tile_world;
     if (my_tiles > 0) {
