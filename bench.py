@@ -47,6 +47,7 @@ def setup_renderer(device):
     cam.setLensModel(host.CLM_THIN_LENS)
     cam.controller().orbitAroundTarget(np.radians(THETA), np.radians(PHI))
     cam.setFStop(FSTOP)
+    r.resetRender()                                                    # as the UI does after camera changes (ui/glwidget.cpp:225-243)
     ctx = r.context()
     ctx.set_selection([-1, -1, -1, 0], [1, 0, 0, 0])                   # no highlighted voxel
     r.requestAction(0.5, 0.5, 0.0, 0.0, host.PA_SELECT_FOCAL_POINT)    # autofocus on the image centre, runs before the next pass
@@ -163,7 +164,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     r, ctx = setup_renderer(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                  # a real (non-default) stream: handle 0 would mean "the context's own"
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     if world > 1:
         r.setPartition(vt.VT_PART_SAMPLES, rank, world)
@@ -232,7 +234,6 @@ def main():
     ee0.record(stream)
     for i in range(e2e_steps):
         r.setVoxelData(vol["res"], vol["grid"], vol["materials"], vol["emissive"])
-        cam = r.camera(); cam.controller().orbitAroundTarget(np.radians(THETA), np.radians(PHI))
         r.renderPasses(PASSES)
         if world > 1:
             reduce_step()

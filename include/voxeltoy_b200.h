@@ -138,6 +138,9 @@ int vt_set_partition(vt_ctx* ctx, int mode, int rank, int world);
 /* sample-partition mode keeps a running SUM instead of an average; expose the device buffer so the caller's
  * collective (NCCL through torch.distributed) can reduce it in place. W*H float4. */
 void* vt_accum_device_ptr(vt_ctx* ctx);
+/* render kernel variant: 0 = one-thread-per-pixel megakernel (default), 1 = persistent per-lane path state machine
+ * (measured slower, kept for the comparison in DESIGN.md); all variants produce identical bits */
+int vt_set_kernel_variant(vt_ctx* ctx, int variant);
 int vt_counters_enable(vt_ctx* ctx, int enable);
 int vt_get_counters(vt_ctx* ctx, vt_counters* out);
 int vt_reset_counters(vt_ctx* ctx);

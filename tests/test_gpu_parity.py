@@ -27,6 +27,16 @@ def _compare(ctx, d, n_passes=1, first=0, integrator=0):
         for n in range(n_passes):
             vto.accumulate(ref, vto.preview_pass(s, first + n), n)
         ref_hits = None
+    # the one-thread-per-pixel megakernel (variant 0) and the persistent path state machine (variant 1, default)
+    # must produce the same bits
+    for variant in (1,):
+        ctx.set_kernel_variant(variant)
+        ctx.reset_accumulation()
+        ctx.render(first, n_passes)
+        got_v = ctx.read_average()
+        hits_v = ctx.read_primary_hits()
+        ctx.set_kernel_variant(0)
+        assert util.same_bits(got, got_v).all() and np.array_equal(hits, hits_v), "kernel variant %d disagrees" % variant
     eq = util.same_bits(got, ref)
     bad = int((~eq).sum())
     if bad:
@@ -217,14 +227,18 @@ def test_counters_match_oracle(vt_ctx):
     d = util.make_frame(util.scene_fall_volume(), 160, 90, bounces=3, theta=120, phi=30)
     s = vto.make_scene(d)
     util.upload(vt_ctx, d)
-    vt_ctx.counters_enable(True)
-    vt_ctx.reset_counters()
-    vt_ctx.render(0, 2)
-    c = vt_ctx.counters()
-    vt_ctx.counters_enable(False)
     S = R = H = 0
     for k in range(2):
         _, _, _, cnt = vto.render_pass(s, k)
         S += cnt["S"]; R += cnt["R"]; H += cnt["Hm"]
-    assert (c["dda_steps"], c["rand_calls"], c["material_evals"]) == (S, R, H)
-    assert c["paths"] == 2 * 160 * 90
+    for variant in (0, 1):
+        vt_ctx.set_kernel_variant(variant)
+        vt_ctx.reset_accumulation()
+        vt_ctx.counters_enable(True)
+        vt_ctx.reset_counters()
+        vt_ctx.render(0, 2)
+        c = vt_ctx.counters()
+        vt_ctx.counters_enable(False)
+        assert (c["dda_steps"], c["rand_calls"], c["material_evals"]) == (S, R, H), variant
+        assert c["paths"] == 2 * 160 * 90
+    vt_ctx.set_kernel_variant(0)

@@ -68,6 +68,7 @@ def test_renderer_c2_flow_env_thin_lens_autofocus(renderer, tmp_path):
     cam.setLensModel(vt.host.CLM_THIN_LENS)
     cam.controller().orbitAroundTarget(np.radians(120), np.radians(30))
     cam.setFStop(2.8)
+    r.resetRender()                      # the UI calls resetRender() after every camera change (ui/glwidget.cpp:225-243)
     ctx = r.context()
     ctx.set_selection([-1, -1, -1, 0], [1, 0, 0, 0])
     r.requestAction(0.5, 0.5, 0, 0, vt.host.PA_SELECT_FOCAL_POINT)
@@ -85,7 +86,7 @@ def test_renderer_c2_flow_env_thin_lens_autofocus(renderer, tmp_path):
     # saveImage flips vertically (renderer.cpp:1132-1136); PFM stores bottom-up, so the file equals GL order
     out = str(tmp_path / "o.pfm")
     r.saveImage(out)
-    assert np.array_equal(vt.host.load_image(out)[::-1], got[..., :3])
+    assert util.same_bits(vt.host.load_image(out)[::-1], got[..., :3]).all()
 
 
 def test_renderer_mesh_tools_and_edit_flow(renderer):

@@ -13,6 +13,12 @@ from tests import util
 
 
 def run(ctx, name, d, passes, reps=3, counters=True):
+    for variant in (0, 1):
+        ctx.set_kernel_variant(variant)
+        _run(ctx, name + " v%d" % variant, d, passes, reps, counters and variant == 1)
+
+
+def _run(ctx, name, d, passes, reps=3, counters=True):
     util.upload(ctx, d)
     ctx.render(0, 1); ctx.sync()
     best = 1e9

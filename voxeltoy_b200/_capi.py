@@ -67,6 +67,7 @@ SIGNATURES = {
     "vt_enable_primary_hits": (C.c_int, [P, C.c_int]),
     "vt_set_partition": (C.c_int, [P, C.c_int, C.c_int, C.c_int]),
     "vt_accum_device_ptr": (C.c_void_p, [P]),
+    "vt_set_kernel_variant": (C.c_int, [P, C.c_int]),
     "vt_counters_enable": (C.c_int, [P, C.c_int]),
     "vt_get_counters": (C.c_int, [P, C.POINTER(VtCounters)]),
     "vt_reset_counters": (C.c_int, [P]),
@@ -275,6 +276,9 @@ class Context:
 
     def accum_device_ptr(self):
         return self.lib.vt_accum_device_ptr(self.h)
+
+    def set_kernel_variant(self, variant):
+        self._ck(self.lib.vt_set_kernel_variant(self.h, int(variant)))
 
     def counters_enable(self, on=True):
         self._ck(self.lib.vt_counters_enable(self.h, int(on)))

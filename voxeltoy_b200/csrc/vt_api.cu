@@ -3,7 +3,7 @@
 // kernels of vt_kernels.cuh. No OpenGL, no CPU fallback: every compute entry point
 // needs a live CUDA context and fails with VT_ERR_CUDA / VT_ERR_NO_DEVICE otherwise.
 #include "../../include/voxeltoy_b200.h"
-#include "vt_kernels.cuh"
+#include "vt_pathstate.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -48,6 +48,8 @@ struct vt_ctx {
     int* d_result = nullptr;
     // partition
     int part_mode = VT_PART_NONE, part_rank = 0, part_world = 1;
+    // render kernel variant: 0 = one-thread-per-pixel megakernel (default), 1 = persistent per-lane path state machine
+    int variant = 0; unsigned int* d_work = nullptr; int ps_blocks[2] = {0, 0};
     // counters
     Counters* d_counters = nullptr; bool count_enabled = false;
     uint64_t paths = 0, launches = 0;
@@ -113,7 +115,7 @@ int vt_create(int device, vt_ctx** out)
     sh.sel_index[0] = sh.sel_index[1] = sh.sel_index[2] = sh.sel_index[3] = 0;   // :723-737
     sh.sel_normal[0] = 1.f; sh.sel_normal[1] = sh.sel_normal[2] = sh.sel_normal[3] = 0.f;
     if (cudaMalloc(&c->d_shared, sizeof(Shared)) != cudaSuccess || cudaMalloc(&c->d_result, 4 * sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&c->d_counters, sizeof(Counters)) != cudaSuccess ||
+        cudaMalloc(&c->d_counters, sizeof(Counters)) != cudaSuccess || cudaMalloc(&c->d_work, sizeof(unsigned int)) != cudaSuccess ||
         cudaMemcpy(c->d_shared, &sh, sizeof sh, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemset(c->d_counters, 0, sizeof(Counters)) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
@@ -138,7 +140,7 @@ void vt_destroy(vt_ctx* c)
     cudaSetDevice(c->device);
     cudaFree(c->d_mat); cudaFree(c->d_bricks); cudaFree(c->d_supers); cudaFree(c->d_materials); cudaFree(c->d_emissive);
     cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum);
-    cudaFree(c->d_primary); cudaFree(c->d_shared); cudaFree(c->d_result); cudaFree(c->d_counters);
+    cudaFree(c->d_primary); cudaFree(c->d_work); cudaFree(c->d_shared); cudaFree(c->d_result); cudaFree(c->d_counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -386,6 +388,10 @@ static Volume make_volume(const vt_ctx* c)
     V.bmax.x = c->bmax[0]; V.bmax.y = c->bmax[1]; V.bmax.z = c->bmax[2];
     V.vsize.x = c->vsize[0]; V.vsize.y = c->vsize[1]; V.vsize.z = c->vsize[2];
     V.resf.x = (float)c->X; V.resf.y = (float)c->Y; V.resf.z = (float)c->Z;
+    {   // dda.h:16 voxelExtent = 1.0 / (boundsMax - boundsMin): binary32 subtraction + division, identical on host and device
+        volatile float ex = c->bmax[0] - c->bmin[0], ey = c->bmax[1] - c->bmin[1], ez = c->bmax[2] - c->bmin[2];
+        V.inv_extent.x = 1.0f / ex; V.inv_extent.y = 1.0f / ey; V.inv_extent.z = 1.0f / ez;
+    }
     // dda.h:98  int(2 * ceil(length(vec3(voxelResolution)))), binary32, unfused
     volatile float xx = V.resf.x * V.resf.x, yy = V.resf.y * V.resf.y, zz = V.resf.z * V.resf.z;
     volatile float s = xx + yy; s = s + zz;
@@ -434,6 +440,13 @@ int vt_set_partition(vt_ctx* c, int mode, int rank, int world)
     return VT_OK;
 }
 
+int vt_set_kernel_variant(vt_ctx* c, int variant)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, variant == 0 || variant == 1, "kernel variant must be 0 (megakernel) or 1 (persistent path state machine)");
+    c->variant = variant;
+    return VT_OK;
+}
 int vt_enable_primary_hits(vt_ctx* c, int enable) { if (!c) return VT_ERR_INVALID; c->primary_enabled = enable != 0; return VT_OK; }
 int vt_counters_enable(vt_ctx* c, int enable) { if (!c) return VT_ERR_INVALID; c->count_enabled = enable != 0; return VT_OK; }
 
@@ -457,10 +470,27 @@ int vt_render(vt_ctx* c, int first_sample, int n_passes)
     const int my_tiles = (tiles - L.tile_rank + L.tile_world - 1) / L.tile_world;
     if (my_tiles > 0) {
         const Volume V = make_volume(c); const Frame F = make_frame(c);
-        const dim3 grid((unsigned)(my_tiles * kCtasPerTile));
         int* prim = c->primary_enabled ? c->d_primary : nullptr;
-        if (c->count_enabled) vt_render_kernel<true><<<grid, 128, 0, c->stream>>>(V, F, L, c->d_accum, prim, c->d_counters);
-        else vt_render_kernel<false><<<grid, 128, 0, c->stream>>>(V, F, L, c->d_accum, prim, c->d_counters);
+        if (c->variant == 0) {
+            const dim3 grid((unsigned)(my_tiles * kCtasPerTile));
+            if (c->count_enabled) vt_render_kernel<true><<<grid, 128, 0, c->stream>>>(V, F, L, c->d_accum, prim, c->d_counters);
+            else vt_render_kernel<false><<<grid, 128, 0, c->stream>>>(V, F, L, c->d_accum, prim, c->d_counters);
+        } else {
+            // persistent: one wave of CTAs sized by occupancy, pixels handed out through a global work counter
+            const int ci = c->count_enabled ? 1 : 0;
+            if (c->ps_blocks[ci] == 0) {
+                int per_sm = 0, sms = 0;
+                if (ci) VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vt_render_ps_kernel<true>, 128, 0));
+                else VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vt_render_ps_kernel<false>, 128, 0));
+                VT_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+                c->ps_blocks[ci] = std::max(1, per_sm) * std::max(1, sms);
+            }
+            const int n_items = my_tiles * kTile * kTile;
+            const int blocks = std::min(c->ps_blocks[ci], (n_items + 127) / 128);
+            VT_CUDA(c, cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), c->stream));
+            if (ci) vt_render_ps_kernel<true><<<blocks, 128, 0, c->stream>>>(V, F, L, n_items, c->d_accum, prim, c->d_counters, c->d_work);
+            else vt_render_ps_kernel<false><<<blocks, 128, 0, c->stream>>>(V, F, L, n_items, c->d_accum, prim, c->d_counters, c->d_work);
+        }
         VT_CUDA(c, cudaGetLastError());
         c->launches += 1;
         if (c->count_enabled) c->paths += (uint64_t)n_passes * (uint64_t)W * H / (c->part_mode == VT_PART_TILES ? c->part_world : 1);

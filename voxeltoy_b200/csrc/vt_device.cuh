@@ -25,6 +25,7 @@ struct Volume {
     int BX, BXY;                           // brick grid strides
     int SX, SXY;                           // super grid strides
     f3 bmin, bmax, vsize, resf;            // world bounds, wsVoxelSize, vec3(voxelResolution)
+    f3 inv_extent;                         // 1.0 / (bmax - bmin)  (dda.h:16, hoisted: same IEEE divisions on the host)
     int max_steps;                         // dda.h:98
 };
 
@@ -147,64 +148,95 @@ __device__ __noinline__ bool raymarch_slow(const Volume& V, f3 vp, f3 dis, f3 sg
     return isect;
 }
 
-// dda.h:7-61. hit_pos is zero on the early-out path (contract U1).
-template <bool COUNT>
-VT_DEV bool raymarch(const Volume& V, f3 o, f3 d, f3& hit_pos, Tally<COUNT>& tl)
+// ---- DDA state machine ------------------------------------------------------------------------
+// The traversal of dda.h:7-61 split into begin / step so that the persistent kernel can interleave the
+// steps of 32 independent rays (vt_pathstate.cuh) while the simple kernels run it to completion.
+// Integer voxel coordinates are exact (0 <= vp < res once the start voxel passed the bounds test);
+// (mask*sign)*inc of dda.h:52 is +-inc = |1/d| for a stepping axis and +-0 otherwise, so the float
+// state `dis` is advanced by exactly the additions the shader performs.
+struct Dda {
+    int ix, iy, iz;            // voxel position (hit position when done)
+    float dx, dy, dz;          // dis
+    float ex, ey, ez;          // sign*inc per axis
+    int sx, sy, sz;            // integer sign
+    int steps;
+    int bkey;                  // cached brick index (-1 none)
+    unsigned long long brick;  // cached 4x4x4 occupancy word
+    int nanmask;               // bit i: component i of the (float) position is NaN (only via the slow path)
+};
+enum { DDA_RUNNING = 0, DDA_HIT = 1, DDA_NOHIT = 2 };
+
+VT_DEV f3 dda_position(const Dda& s)
 {
-    hit_pos = mk3(0.0f);
-    const f3 ext = mk3(1.0f) / (V.bmax - V.bmin);                 // :16
+    const float qn = __int_as_float(0x7fc00000);
+    return mk3((s.nanmask & 1) ? qn : (float)s.ix, (s.nanmask & 2) ? qn : (float)s.iy, (s.nanmask & 4) ? qn : (float)s.iz);
+}
+
+// dda.h:16-34. Returns DDA_RUNNING when stepping must follow, else the final status (position in s).
+template <bool COUNT>
+VT_DEV int dda_begin(const Volume& V, f3 o, f3 d, Dda& s, Tally<COUNT>& tl)
+{
+    s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.steps = 0; s.bkey = -1; s.brick = 0ull;   // hit_pos = 0 on the early-out path (contract U1)
     o = o + gsign(d) * 0.001f;                                    // :19
-    const f3 vo = ((o - V.bmin) * ext) * V.resf;                  // :20
+    const f3 vo = ((o - V.bmin) * V.inv_extent) * V.resf;         // :16,:20
     const f3 vp = gfloor(vo);                                     // :22
-    if (out_of_grid(vp, V.resf)) return false;                    // :24-25
+    if (out_of_grid(vp, V.resf)) return DDA_NOHIT;                // :24-25
     // :29  mix(d, 1e-5, step(abs(d), 1e-5))
     d = mk3(gmix(d.x, 1e-5f, gstep(gabs(d.x), 1e-5f)),
             gmix(d.y, 1e-5f, gstep(gabs(d.y), 1e-5f)),
             gmix(d.z, 1e-5f, gstep(gabs(d.z), 1e-5f)));
     const f3 inc = mk3(1.0f) / d;                                 // :31
     const f3 sg = gsign(d);                                       // :32
-    f3 dis = (((vp - vo) + 0.5f) + sg * 0.5f) * inc;              // :34
-
-    if (vp.x != vp.x || vp.y != vp.y || vp.z != vp.z)             // NaN start voxel passes the bounds test of :24
-        return raymarch_slow<COUNT>(V, vp, dis, sg, inc, hit_pos, tl);
-
-    // Integer voxel coordinates (exact: 0 <= vp < res) and per-axis increments.
-    // (mask*sign)*inc of dda.h:52 is +-inc = |1/d| for a stepping axis and +-0 otherwise.
-    int ix = f2i(vp.x), iy = f2i(vp.y), iz = f2i(vp.z);
-    const int sx = f2i(sg.x), sy = f2i(sg.y), sz = f2i(sg.z);
-    const float ex = sg.x * inc.x, ey = sg.y * inc.y, ez = sg.z * inc.z;
-    float dx = dis.x, dy = dis.y, dz = dis.z;
-
-    bool isect = false;
-    int bkey = -1, skey = -1;
-    unsigned long long brick = 0ull, super = 0ull;
-    int steps = 0;
-    const int max_steps = V.max_steps;
-    while (steps < max_steps) {                                   // :38
-        if ((unsigned)ix >= (unsigned)V.X || (unsigned)iy >= (unsigned)V.Y || (unsigned)iz >= (unsigned)V.Z) break; // :41-42
-        const int bx = ix >> 2, by = iy >> 2, bz = iz >> 2;
-        const int key = bx + by * V.BX + bz * V.BXY;
-        if (key != bkey) {
-            bkey = key;
-            const int sk = (bx >> 2) + (by >> 2) * V.SX + (bz >> 2) * V.SXY;
-            if (sk != skey) { skey = sk; super = __ldg(V.supers + sk); }
-            const int sbit = (bx & 3) | ((by & 3) << 2) | ((bz & 3) << 4);
-            brick = ((super >> sbit) & 1ull) ? __ldg(V.bricks + key) : 0ull;
-        }
-        VT_TALLY(S, 1);
-        const int bit = (ix & 3) | ((iy & 3) << 2) | ((iz & 3) << 4);
-        if ((brick >> bit) & 1ull) { isect = true; break; }       // :44-50
-        // :51 mask = step(dis.xyz, dis.yxy) * step(dis.xyz, dis.zzx)   (ties step several axes)
-        const bool mx = !(dy < dx) && !(dz < dx);
-        const bool my = !(dx < dy) && !(dz < dy);
-        const bool mz = !(dy < dz) && !(dx < dz);
-        if (mx) { dx = dx + ex; ix += sx; }                        // :52-53
-        if (my) { dy = dy + ey; iy += sy; }
-        if (mz) { dz = dz + ez; iz += sz; }
-        ++steps;
+    const f3 dis = (((vp - vo) + 0.5f) + sg * 0.5f) * inc;        // :34
+    if (vp.x != vp.x || vp.y != vp.y || vp.z != vp.z) {           // a NaN start voxel passes the bounds test of :24
+        f3 hp;
+        const bool isect = raymarch_slow<COUNT>(V, vp, dis, sg, inc, hp, tl);
+        s.nanmask = (hp.x != hp.x ? 1 : 0) | (hp.y != hp.y ? 2 : 0) | (hp.z != hp.z ? 4 : 0);
+        s.ix = f2i(hp.x); s.iy = f2i(hp.y); s.iz = f2i(hp.z);
+        return isect ? DDA_HIT : DDA_NOHIT;
     }
-    hit_pos = mk3((float)ix, (float)iy, (float)iz);               // :59
-    return isect;
+    s.ix = f2i(vp.x); s.iy = f2i(vp.y); s.iz = f2i(vp.z);
+    s.sx = f2i(sg.x); s.sy = f2i(sg.y); s.sz = f2i(sg.z);
+    s.ex = sg.x * inc.x; s.ey = sg.y * inc.y; s.ez = sg.z * inc.z;
+    s.dx = dis.x; s.dy = dis.y; s.dz = dis.z;
+    return DDA_RUNNING;
+}
+
+// one iteration of the while loop of dda.h:38-57
+template <bool COUNT>
+VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
+{
+    if ((unsigned)s.ix >= (unsigned)V.X || (unsigned)s.iy >= (unsigned)V.Y || (unsigned)s.iz >= (unsigned)V.Z) return DDA_NOHIT;   // :41-42
+    const int bx = s.ix >> 2, by = s.iy >> 2, bz = s.iz >> 2;
+    const int key = bx + by * V.BX + bz * V.BXY;
+    if (key != s.bkey) {
+        s.bkey = key;
+        const unsigned long long super = __ldg(V.supers + ((bx >> 2) + (by >> 2) * V.SX + (bz >> 2) * V.SXY));
+        const int sbit = (bx & 3) | ((by & 3) << 2) | ((bz & 3) << 4);
+        s.brick = ((super >> sbit) & 1ull) ? __ldg(V.bricks + key) : 0ull;
+    }
+    VT_TALLY(S, 1);
+    const int bit = (s.ix & 3) | ((s.iy & 3) << 2) | ((s.iz & 3) << 4);
+    if ((s.brick >> bit) & 1ull) return DDA_HIT;                  // :44-50
+    // :51 mask = step(dis.xyz, dis.yxy) * step(dis.xyz, dis.zzx)   (ties step several axes at once)
+    const bool mx = !(s.dy < s.dx) && !(s.dz < s.dx);
+    const bool my = !(s.dx < s.dy) && !(s.dz < s.dy);
+    const bool mz = !(s.dy < s.dz) && !(s.dx < s.dz);
+    if (mx) { s.dx = s.dx + s.ex; s.ix += s.sx; }                 // :52-53
+    if (my) { s.dy = s.dy + s.ey; s.iy += s.sy; }
+    if (mz) { s.dz = s.dz + s.ez; s.iz += s.sz; }
+    return (++s.steps < V.max_steps) ? DDA_RUNNING : DDA_NOHIT;   // :38,:55
+}
+
+// dda.h:7-61 run to completion
+template <bool COUNT>
+VT_DEV bool raymarch(const Volume& V, f3 o, f3 d, f3& hit_pos, Tally<COUNT>& tl)
+{
+    Dda s;
+    int st = dda_begin<COUNT>(V, o, d, s, tl);
+    while (st == DDA_RUNNING) st = dda_step<COUNT>(V, s, tl);
+    hit_pos = dda_position(s);
+    return st == DDA_HIT;
 }
 
 // dda.h:63-100
@@ -546,6 +578,7 @@ VT_DEV f3 emission_material(const Frame& F, int off, Tally<COUNT>& tl)          
 // ----------------------------------------------------------------------------------
 // integrator pieces shared by pathTracer.fs and editMode.fs
 // ----------------------------------------------------------------------------------
+
 VT_DEV void voxel_index_to_pos(int idx, int X, int Y, int& x, int& y, int& z)          // coordinates.h:118-128
 {
     const int dz = X * Y, dy = X;
@@ -554,21 +587,28 @@ VT_DEV void voxel_index_to_pos(int idx, int X, int Y, int& x, int& y, int& z)   
     x = idx;
 }
 
+// pathTracer.fs:64-170 split at the shadow ray, so that the persistent kernel can trace it as a queued segment.
+struct LightSample {
+    f4 wl;          // direction to the light + pdf (already divided by the number of lights, :124)
+    f3 L;           // radiance arriving from the sampled light
+    int target;     // linear index of the sampled emissive voxel, -1 = environment
+};
 template <bool COUNT>
-VT_DEV f3 direct_lighting(const Volume& V, const Frame& F, int mat_off, const Basis& hb, f3 wo, int2& rng, Tally<COUNT>& tl)   // pathTracer.fs:64-170
+VT_DEV LightSample sample_light(const Volume& V, const Frame& F, const Basis& hb, int2& rng, Tally<COUNT>& tl)   // :69-124
 {
-    f4 wl = mk4(0.f, 0.f, 0.f, 0.f);
-    f3 L;
-    int ex = 0, ey = 0, ez = 0;
+    LightSample ls;
+    ls.wl = mk4(0.f, 0.f, 0.f, 0.f);
+    ls.target = -1;
     const f4 u = rng_next<COUNT>(F, rng, tl);                     // :77
     const int num_lights = F.n_emissive + 1;                      // :78
     const int light_index = f2i(u.x * (float)num_lights);         // :79
-    const bool sampling_voxel = light_index < num_lights - 1;     // :81
-    if (sampling_voxel) {
+    if (light_index < num_lights - 1) {                           // :81
         const int eidx = __ldg(F.emissive + light_index);         // :85
+        int ex, ey, ez;
         voxel_index_to_pos(eidx, V.X, V.Y, ex, ey, ez);           // :86
+        ls.target = ex + ey * V.X + ez * V.X * V.Y;
         const int eoff = fetch_offset(V, ex, ey, ez);             // :87
-        L = mk3(10.0f) * emission_material<COUNT>(F, eoff, tl);   // :88
+        ls.L = mk3(10.0f) * emission_material<COUNT>(F, eoff, tl);   // :88
         const f3 vse = mk3((float)ex, (float)ey, (float)ez);
         f3 ep = (vse / V.resf) * (V.bmax - V.bmin) + V.bmin;      // :90
         ep = ep + mk3(u.y, u.z, u.w) * V.vsize;                   // :92
@@ -579,25 +619,43 @@ VT_DEV f3 direct_lighting(const Volume& V, const Frame& F, int mat_off, const Ba
         voxel_to_world(V, vse, hb.position, w, lb);               // :103-106
         const float area = 6.0f * V.vsize.x * V.vsize.y;          // :113
         const float jac = (r * r) / gabs(dot(-w, lb.normal));     // :114
-        wl = mk4(w, jac / area);                                  // :115
+        ls.wl = mk4(w, jac / area);                               // :115
     } else {
-        L = sample_env<COUNT>(F, hb, u.y, u.z, wl, tl);           // :120
+        ls.L = sample_env<COUNT>(F, hb, u.y, u.z, ls.wl, tl);     // :120
     }
-    wl.w = wl.w / (float)num_lights;                              // :124
-    const f3 wdir = xyz(wl);
-    f3 shadow_hit; bool hit_ground;
-    const bool missed = !traverse<COUNT>(V, hb.position, wdir, shadow_hit, hit_ground, tl);   // :133
-    if (sampling_voxel) {
-        if (missed || shadow_hit.x != (float)ex || shadow_hit.y != (float)ey || shadow_hit.z != (float)ez)
-            return mk3(0.0f);                                     // :138-142
-    } else {
-        if (!missed) return mk3(0.0f);                            // :148-152
+    ls.wl.w = ls.wl.w / (float)num_lights;                        // :124
+    return ls;
+}
+// :133-153: is the sampled light hidden, given the result of the shadow traversal
+VT_DEV bool light_occluded(const Volume& V, int target, bool shadow_hit_something, f3 shadow_hit)
+{
+    if (target >= 0) {
+        int ex, ey, ez;
+        voxel_index_to_pos(target, V.X, V.Y, ex, ey, ez);
+        return !shadow_hit_something || shadow_hit.x != (float)ex || shadow_hit.y != (float)ey || shadow_hit.z != (float)ez;
     }
+    return shadow_hit_something;
+}
+// :155-164: contribution of a visible light sample
+template <bool COUNT>
+VT_DEV f3 light_contribution(const Frame& F, int mat_off, const Basis& hb, f3 wo, const LightSample& ls, Tally<COUNT>& tl)
+{
+    const f3 wdir = xyz(ls.wl);
     const f3 lsWo = world_to_local(wo, hb);                       // :159
     const f3 lsWi = world_to_local(wdir, hb);
     const f4 bf = evaluate_material<COUNT>(F, mat_off, lsWo, lsWi, tl);     // :161
-    const float mis = power_heuristic(wl.w, bf.w);                // :163
-    return xyz(bf) * L * gabs(dot(wdir, hb.normal)) * mis / wl.w; // :164
+    const float mis = power_heuristic(ls.wl.w, bf.w);             // :163
+    return xyz(bf) * ls.L * gabs(dot(wdir, hb.normal)) * mis / ls.wl.w;   // :164
+}
+
+template <bool COUNT>
+VT_DEV f3 direct_lighting(const Volume& V, const Frame& F, int mat_off, const Basis& hb, f3 wo, int2& rng, Tally<COUNT>& tl)   // pathTracer.fs:64-170
+{
+    const LightSample ls = sample_light<COUNT>(V, F, hb, rng, tl);
+    f3 shadow_hit; bool hit_ground;
+    const bool hit_something = traverse<COUNT>(V, hb.position, xyz(ls.wl), shadow_hit, hit_ground, tl);   // :133
+    if (light_occluded(V, ls.target, hit_something, shadow_hit)) return mk3(0.0f);                       // :134-153
+    return light_contribution<COUNT>(F, mat_off, hb, wo, ls, tl);
 }
 
 VT_DEV f3 tonemap(f3 rad)                                         // pathTracer.fs:294 (exposure 1, gamma 2.2: :43-44)

@@ -27,7 +27,7 @@ struct RenderLaunch {
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 vt_render_kernel(const Volume V, const Frame F, const RenderLaunch L,
                  float4* __restrict__ accum, int* __restrict__ primary, Counters* __restrict__ counters)
 {
