@@ -138,9 +138,13 @@ int vt_set_partition(vt_ctx* ctx, int mode, int rank, int world);
 /* sample-partition mode keeps a running SUM instead of an average; expose the device buffer so the caller's
  * collective (NCCL through torch.distributed) can reduce it in place. W*H float4. */
 void* vt_accum_device_ptr(vt_ctx* ctx);
-/* render kernel variant: 0 = one-thread-per-pixel megakernel (default), 1 = persistent per-lane path state machine
- * (measured slower, kept for the comparison in DESIGN.md); all variants produce identical bits */
+/* render kernel variant: 0 = one-thread-per-pixel megakernel, 1 = persistent per-lane path state machine (measured
+ * slower, kept for the comparison in DESIGN.md), 2 = wavefront with per-material shade queues and self-refilling
+ * trace warps (default); all variants produce identical bits */
 int vt_set_kernel_variant(vt_ctx* ctx, int variant);
+/* wavefront variant: upper bound on the paths (pixel-passes) in flight per batch; the passes of one vt_render call are
+ * split into batches of floor(max_paths / pixels) passes (at least 1). Tuning knob, no effect on results. */
+int vt_set_wavefront_max_paths(vt_ctx* ctx, size_t max_paths);
 int vt_counters_enable(vt_ctx* ctx, int enable);
 int vt_get_counters(vt_ctx* ctx, vt_counters* out);
 int vt_reset_counters(vt_ctx* ctx);

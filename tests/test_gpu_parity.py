@@ -27,15 +27,18 @@ def _compare(ctx, d, n_passes=1, first=0, integrator=0):
         for n in range(n_passes):
             vto.accumulate(ref, vto.preview_pass(s, first + n), n)
         ref_hits = None
-    # the one-thread-per-pixel megakernel (variant 0) and the persistent path state machine (variant 1, default)
-    # must produce the same bits
-    for variant in (1,):
+    # the wavefront renderer (variant 2, default; also with a path budget that splits the passes into several
+    # batches), the one-thread-per-pixel megakernel (0) and the persistent path state machine (1) must produce the same bits
+    for variant, budget in ((0, 0), (1, 0), (2, 2 * 4096)):
         ctx.set_kernel_variant(variant)
+        if budget:
+            ctx.set_wavefront_max_paths(budget)
         ctx.reset_accumulation()
         ctx.render(first, n_passes)
         got_v = ctx.read_average()
         hits_v = ctx.read_primary_hits()
-        ctx.set_kernel_variant(0)
+        ctx.set_kernel_variant(2)
+        ctx.set_wavefront_max_paths(8 << 20)
         assert util.same_bits(got, got_v).all() and np.array_equal(hits, hits_v), "kernel variant %d disagrees" % variant
     eq = util.same_bits(got, ref)
     bad = int((~eq).sum())
@@ -231,7 +234,7 @@ def test_counters_match_oracle(vt_ctx):
     for k in range(2):
         _, _, _, cnt = vto.render_pass(s, k)
         S += cnt["S"]; R += cnt["R"]; H += cnt["Hm"]
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         vt_ctx.set_kernel_variant(variant)
         vt_ctx.reset_accumulation()
         vt_ctx.counters_enable(True)
@@ -241,4 +244,4 @@ def test_counters_match_oracle(vt_ctx):
         vt_ctx.counters_enable(False)
         assert (c["dda_steps"], c["rand_calls"], c["material_evals"]) == (S, R, H), variant
         assert c["paths"] == 2 * 160 * 90
-    vt_ctx.set_kernel_variant(0)
+    vt_ctx.set_kernel_variant(2)

@@ -13,9 +13,9 @@ from tests import util
 
 
 def run(ctx, name, d, passes, reps=3, counters=True):
-    for variant in (0, 1):
+    for variant in (0, 2):
         ctx.set_kernel_variant(variant)
-        _run(ctx, name + " v%d" % variant, d, passes, reps, counters and variant == 1)
+        _run(ctx, name + " v%d" % variant, d, passes, reps, counters and variant == 2)
 
 
 def _run(ctx, name, d, passes, reps=3, counters=True):

@@ -68,6 +68,7 @@ SIGNATURES = {
     "vt_set_partition": (C.c_int, [P, C.c_int, C.c_int, C.c_int]),
     "vt_accum_device_ptr": (C.c_void_p, [P]),
     "vt_set_kernel_variant": (C.c_int, [P, C.c_int]),
+    "vt_set_wavefront_max_paths": (C.c_int, [P, C.c_size_t]),
     "vt_counters_enable": (C.c_int, [P, C.c_int]),
     "vt_get_counters": (C.c_int, [P, C.POINTER(VtCounters)]),
     "vt_reset_counters": (C.c_int, [P]),
@@ -279,6 +280,9 @@ class Context:
 
     def set_kernel_variant(self, variant):
         self._ck(self.lib.vt_set_kernel_variant(self.h, int(variant)))
+
+    def set_wavefront_max_paths(self, n):
+        self._ck(self.lib.vt_set_wavefront_max_paths(self.h, int(n)))
 
     def counters_enable(self, on=True):
         self._ck(self.lib.vt_counters_enable(self.h, int(on)))

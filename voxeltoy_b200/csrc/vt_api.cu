@@ -4,6 +4,7 @@
 // needs a live CUDA context and fails with VT_ERR_CUDA / VT_ERR_NO_DEVICE otherwise.
 #include "../../include/voxeltoy_b200.h"
 #include "vt_pathstate.cuh"
+#include "vt_wavefront.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -49,7 +50,12 @@ struct vt_ctx {
     // partition
     int part_mode = VT_PART_NONE, part_rank = 0, part_world = 1;
     // render kernel variant: 0 = one-thread-per-pixel megakernel (default), 1 = persistent per-lane path state machine
-    int variant = 0; unsigned int* d_work = nullptr; int ps_blocks[2] = {0, 0};
+    // 2 = wavefront (vt_wavefront.cuh, default for the path tracer)
+    int variant = 2; unsigned int* d_work = nullptr; int ps_blocks[2] = {0, 0};
+    // wavefront state (variant 2): SoA path state + queues, sized for wf_capacity paths
+    WfState wf{}; void* d_wf_pool = nullptr; size_t wf_capacity = 0; size_t wf_max_paths = (size_t)8 << 20;
+    WfCounts* d_wf_counts = nullptr; int wf_counts_cap = 0;
+    int wf_shade_blocks[2] = {0, 0}, wf_trace_blocks[2] = {0, 0};
     // counters
     Counters* d_counters = nullptr; bool count_enabled = false;
     uint64_t paths = 0, launches = 0;
@@ -110,6 +116,8 @@ int vt_create(int device, vt_ctx** out)
         delete c; return VT_ERR_CUDA;
     }
     c->stream = c->own_stream;
+    if (const char* e = getenv("VT_WF_MAX_PATHS")) { const long long v = atoll(e); if (v > 0) c->wf_max_paths = (size_t)v; }   // tuning knob
+    if (const char* e = getenv("VT_KERNEL_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->variant = v; }
     Shared sh;
     sh.focal_distance = 99999999.0f;                                  // renderer.cpp:712-720
     sh.sel_index[0] = sh.sel_index[1] = sh.sel_index[2] = sh.sel_index[3] = 0;   // :723-737
@@ -140,6 +148,7 @@ void vt_destroy(vt_ctx* c)
     cudaSetDevice(c->device);
     cudaFree(c->d_mat); cudaFree(c->d_bricks); cudaFree(c->d_supers); cudaFree(c->d_materials); cudaFree(c->d_emissive);
     cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum);
+    cudaFree(c->d_wf_pool); cudaFree(c->d_wf_counts);
     cudaFree(c->d_primary); cudaFree(c->d_work); cudaFree(c->d_shared); cudaFree(c->d_result); cudaFree(c->d_counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -443,12 +452,87 @@ int vt_set_partition(vt_ctx* c, int mode, int rank, int world)
 int vt_set_kernel_variant(vt_ctx* c, int variant)
 {
     if (!c) return VT_ERR_INVALID;
-    VT_REQ(c, variant == 0 || variant == 1, "kernel variant must be 0 (megakernel) or 1 (persistent path state machine)");
+    VT_REQ(c, variant >= 0 && variant <= 2, "kernel variant must be 0 (megakernel), 1 (persistent path state machine) or 2 (wavefront)");
     c->variant = variant;
+    return VT_OK;
+}
+int vt_set_wavefront_max_paths(vt_ctx* c, size_t n)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, n > 0, "path budget must be positive");
+    c->wf_max_paths = n;
     return VT_OK;
 }
 int vt_enable_primary_hits(vt_ctx* c, int enable) { if (!c) return VT_ERR_INVALID; c->primary_enabled = enable != 0; return VT_OK; }
 int vt_counters_enable(vt_ctx* c, int enable) { if (!c) return VT_ERR_INVALID; c->count_enabled = enable != 0; return VT_OK; }
+
+} // extern "C" (the wavefront driver is a template)
+
+// ---- wavefront driver (variant 2, vt_wavefront.cuh) -------------------------------------------------------
+static int wf_reserve(vt_ctx* c, size_t n_paths, int n_iters)
+{
+    if (n_paths > c->wf_capacity) {
+        VT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_wf_pool); c->d_wf_pool = nullptr; c->wf_capacity = 0;
+        // 8 x 16-byte arrays, vis, 6 queues: 156 bytes per path
+        const size_t bytes = n_paths * (8 * 16 + 4 + (kWfQueues + 1) * 4);
+        VT_CUDA(c, cudaMalloc(&c->d_wf_pool, bytes));
+        char* p = (char*)c->d_wf_pool;
+        auto take = [&](size_t b) { char* r = p; p += b; return (void*)r; };
+        c->wf.ray0 = (float4*)take(n_paths * 16); c->wf.ray1 = (float4*)take(n_paths * 16); c->wf.shadow = (float4*)take(n_paths * 16);
+        c->wf.rad0 = (float4*)take(n_paths * 16); c->wf.rad1 = (float4*)take(n_paths * 16); c->wf.rad2 = (float4*)take(n_paths * 16);
+        c->wf.hit = (int4*)take(n_paths * 16); c->wf.samples = (float4*)take(n_paths * 16);
+        c->wf.vis = (int*)take(n_paths * 4);
+        for (int k = 0; k < kWfQueues; ++k) c->wf.sq[k] = (unsigned int*)take(n_paths * 4);
+        c->wf.tq = (unsigned int*)take(n_paths * 4);
+        c->wf_capacity = n_paths;
+    }
+    if (n_iters > c->wf_counts_cap) {
+        VT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_wf_counts); c->d_wf_counts = nullptr;
+        VT_CUDA(c, cudaMalloc(&c->d_wf_counts, sizeof(WfCounts) * (size_t)n_iters));
+        c->wf_counts_cap = n_iters;
+    }
+    return VT_OK;
+}
+
+template <bool COUNT>
+static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLaunch& L, int my_tiles, int* prim)
+{
+    const int ci = COUNT ? 1 : 0;
+    if (c->wf_shade_blocks[ci] == 0) {
+        int per_sm_s = 0, per_sm_t = 0, sms = 0;
+        VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, wf_shade_kernel<COUNT>, 128, 0));
+        VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, wf_trace_kernel<COUNT>, 256, 0));
+        VT_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        c->wf_shade_blocks[ci] = std::max(1, per_sm_s) * std::max(1, sms);
+        c->wf_trace_blocks[ci] = std::max(1, per_sm_t) * std::max(1, sms);
+    }
+    const int n_items = my_tiles * kTile * kTile;
+    const int batch_max = (int)std::max<size_t>(1, c->wf_max_paths / (size_t)n_items);
+    const int n_iters = F.max_bounces + 2;
+    int rc = wf_reserve(c, (size_t)n_items * (size_t)std::min(batch_max, L.n_passes), n_iters);
+    if (rc != VT_OK) return rc;
+    WfState S = c->wf; S.n_items = n_items;
+    for (int pass0 = 0; pass0 < L.n_passes; pass0 += batch_max) {
+        const int nb = std::min(batch_max, L.n_passes - pass0);
+        VT_CUDA(c, cudaMemsetAsync(c->d_wf_counts, 0, sizeof(WfCounts) * (size_t)n_iters, c->stream));
+        wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 128), (unsigned)nb), 128, 0, c->stream>>>(V, F, L, S, pass0, c->d_wf_counts, prim, c->d_counters);
+        c->launches += 1;
+        for (int it = 0; it <= F.max_bounces; ++it) {
+            wf_shade_kernel<COUNT><<<c->wf_shade_blocks[ci], 128, 0, c->stream>>>(V, F, S, it == 0 ? 1 : 0, c->d_wf_counts + it, c->d_wf_counts + it, c->d_counters);
+            c->launches += 1;
+            if (it == F.max_bounces) break;
+            wf_trace_kernel<COUNT><<<c->wf_trace_blocks[ci], 256, 0, c->stream>>>(V, F, S, c->d_wf_counts + it, c->d_wf_counts + it + 1, c->d_counters);
+            c->launches += 1;
+        }
+        wf_accumulate_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, c->stream>>>(F, L, S, pass0, nb, c->d_accum);
+        c->launches += 1;
+    }
+    return VT_OK;
+}
+
+extern "C" {
 
 int vt_render(vt_ctx* c, int first_sample, int n_passes)
 {
@@ -471,7 +555,11 @@ int vt_render(vt_ctx* c, int first_sample, int n_passes)
     if (my_tiles > 0) {
         const Volume V = make_volume(c); const Frame F = make_frame(c);
         int* prim = c->primary_enabled ? c->d_primary : nullptr;
-        if (c->variant == 0) {
+        if (c->variant == 2 && L.integrator == VT_INTEGRATOR_PATHTRACER) {
+            const int rc = c->count_enabled ? wf_render<true>(c, V, F, L, my_tiles, prim) : wf_render<false>(c, V, F, L, my_tiles, prim);
+            if (rc != VT_OK) return rc;
+            c->launches -= 1;          // the common epilogue below counts one launch
+        } else if (c->variant != 1) {
             const dim3 grid((unsigned)(my_tiles * kCtasPerTile));
             if (c->count_enabled) vt_render_kernel<true><<<grid, 128, 0, c->stream>>>(V, F, L, c->d_accum, prim, c->d_counters);
             else vt_render_kernel<false><<<grid, 128, 0, c->stream>>>(V, F, L, c->d_accum, prim, c->d_counters);
