@@ -1,5 +1,6 @@
 """Developer timing script (not the contract bench): times vt_render on a few configurations with wall clock
 around vt_sync. Usage: python tools/quick_bench.py [config ...]"""
+import os
 import sys
 import time
 
@@ -13,12 +14,13 @@ from tests import util
 
 
 def run(ctx, name, d, passes, reps=3, counters=True):
-    for variant in (0, 2):
+    for variant in [int(v) for v in os.environ.get("VT_QB_VARIANTS", "0,2").split(",")]:
         ctx.set_kernel_variant(variant)
         _run(ctx, name + " v%d" % variant, d, passes, reps, counters and variant == 2)
 
 
 def _run(ctx, name, d, passes, reps=3, counters=True):
+    reps = int(os.environ.get("VT_QB_REPS", reps))
     util.upload(ctx, d)
     ctx.render(0, 1); ctx.sync()
     best = 1e9

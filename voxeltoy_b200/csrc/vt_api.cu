@@ -55,7 +55,7 @@ struct vt_ctx {
     // wavefront state (variant 2): SoA path state + queues, sized for wf_capacity paths
     WfState wf{}; void* d_wf_pool = nullptr; size_t wf_capacity = 0; size_t wf_max_paths = (size_t)8 << 20;
     WfCounts* d_wf_counts = nullptr; int wf_counts_cap = 0;
-    int wf_shade_blocks[2] = {0, 0}, wf_trace_blocks[2] = {0, 0};
+    int wf_shade_blocks[2] = {0, 0}, wf_trace_blocks[2] = {0, 0}, wf_sms = 0;
     // counters
     Counters* d_counters = nullptr; bool count_enabled = false;
     uint64_t paths = 0, launches = 0;
@@ -474,14 +474,15 @@ static int wf_reserve(vt_ctx* c, size_t n_paths, int n_iters)
     if (n_paths > c->wf_capacity) {
         VT_CUDA(c, cudaStreamSynchronize(c->stream));
         cudaFree(c->d_wf_pool); c->d_wf_pool = nullptr; c->wf_capacity = 0;
-        // 8 x 16-byte arrays, vis, 6 queues: 156 bytes per path
-        const size_t bytes = n_paths * (8 * 16 + 4 + (kWfQueues + 1) * 4);
+        // 7 x 16-byte path arrays, 2 x 48-byte ray records, vis, 6 queues: 236 bytes per path
+        const size_t bytes = n_paths * (7 * 16 + 2 * 48 + 4 + (kWfQueues + 1) * 4);
         VT_CUDA(c, cudaMalloc(&c->d_wf_pool, bytes));
         char* p = (char*)c->d_wf_pool;
         auto take = [&](size_t b) { char* r = p; p += b; return (void*)r; };
-        c->wf.ray0 = (float4*)take(n_paths * 16); c->wf.ray1 = (float4*)take(n_paths * 16); c->wf.shadow = (float4*)take(n_paths * 16);
+        c->wf.ray0 = (float4*)take(n_paths * 16); c->wf.ray1 = (float4*)take(n_paths * 16);
         c->wf.rad0 = (float4*)take(n_paths * 16); c->wf.rad1 = (float4*)take(n_paths * 16); c->wf.rad2 = (float4*)take(n_paths * 16);
         c->wf.hit = (int4*)take(n_paths * 16); c->wf.samples = (float4*)take(n_paths * 16);
+        c->wf.rq0 = (int4*)take(n_paths * 32); c->wf.rq1 = (float4*)take(n_paths * 32); c->wf.rq2 = (float4*)take(n_paths * 32);
         c->wf.vis = (int*)take(n_paths * 4);
         for (int k = 0; k < kWfQueues; ++k) c->wf.sq[k] = (unsigned int*)take(n_paths * 4);
         c->wf.tq = (unsigned int*)take(n_paths * 4);
@@ -507,6 +508,7 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
         VT_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
         c->wf_shade_blocks[ci] = std::max(1, per_sm_s) * std::max(1, sms);
         c->wf_trace_blocks[ci] = std::max(1, per_sm_t) * std::max(1, sms);
+        c->wf_sms = std::max(1, sms);
     }
     const int n_items = my_tiles * kTile * kTile;
     const int batch_max = (int)std::max<size_t>(1, c->wf_max_paths / (size_t)n_items);
@@ -514,17 +516,20 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
     int rc = wf_reserve(c, (size_t)n_items * (size_t)std::min(batch_max, L.n_passes), n_iters);
     if (rc != VT_OK) return rc;
     WfState S = c->wf; S.n_items = n_items;
+    WfCounts* cn = c->d_wf_counts;
+    const int classify_blocks = c->wf_sms * 8;
     for (int pass0 = 0; pass0 < L.n_passes; pass0 += batch_max) {
         const int nb = std::min(batch_max, L.n_passes - pass0);
-        VT_CUDA(c, cudaMemsetAsync(c->d_wf_counts, 0, sizeof(WfCounts) * (size_t)n_iters, c->stream));
-        wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 128), (unsigned)nb), 128, 0, c->stream>>>(V, F, L, S, pass0, c->d_wf_counts, prim, c->d_counters);
+        VT_CUDA(c, cudaMemsetAsync(cn, 0, sizeof(WfCounts) * (size_t)n_iters, c->stream));
+        wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 256), (unsigned)nb), 256, 0, c->stream>>>(V, F, L, S, pass0, cn, cn + 1, prim, c->d_counters);
         c->launches += 1;
-        for (int it = 0; it <= F.max_bounces; ++it) {
-            wf_shade_kernel<COUNT><<<c->wf_shade_blocks[ci], 128, 0, c->stream>>>(V, F, S, it == 0 ? 1 : 0, c->d_wf_counts + it, c->d_wf_counts + it, c->d_counters);
-            c->launches += 1;
+        for (int it = 0; ; ++it) {
+            // it == 0: primary rays; it >= 1: the shadow + bounce rays emitted by wf_shade(it)
+            wf_trace_kernel<COUNT><<<c->wf_trace_blocks[ci], 256, 0, c->stream>>>(V, S, cn + it, c->d_counters);
+            wf_classify_kernel<<<classify_blocks, 256, 0, c->stream>>>(V, F, L, S, pass0, cn + it, cn + it + 1, it == 0 ? prim : nullptr);
+            wf_shade_kernel<COUNT><<<c->wf_shade_blocks[ci], 128, 0, c->stream>>>(V, F, S, cn + it + 1, c->d_counters);
+            c->launches += 3;
             if (it == F.max_bounces) break;
-            wf_trace_kernel<COUNT><<<c->wf_trace_blocks[ci], 256, 0, c->stream>>>(V, F, S, c->d_wf_counts + it, c->d_wf_counts + it + 1, c->d_counters);
-            c->launches += 1;
         }
         wf_accumulate_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, c->stream>>>(F, L, S, pass0, nb, c->d_accum);
         c->launches += 1;

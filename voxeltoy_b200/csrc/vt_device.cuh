@@ -202,22 +202,18 @@ VT_DEV int dda_begin(const Volume& V, f3 o, f3 d, Dda& s, Tally<COUNT>& tl)
     return DDA_RUNNING;
 }
 
-// one iteration of the while loop of dda.h:38-57
+// one iteration of the while loop of dda.h:38-57. Branch-free apart from the two exits: the 4x4x4 occupancy word is
+// re-loaded under a predicate when the voxel moved to another brick (about 4 steps in 10), so a warp whose lanes are at
+// different places in their bricks still issues one common instruction stream per step.
 template <bool COUNT>
 VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
 {
     if ((unsigned)s.ix >= (unsigned)V.X || (unsigned)s.iy >= (unsigned)V.Y || (unsigned)s.iz >= (unsigned)V.Z) return DDA_NOHIT;   // :41-42
-    const int bx = s.ix >> 2, by = s.iy >> 2, bz = s.iz >> 2;
-    const int key = bx + by * V.BX + bz * V.BXY;
-    if (key != s.bkey) {
-        s.bkey = key;
-        const unsigned long long super = __ldg(V.supers + ((bx >> 2) + (by >> 2) * V.SX + (bz >> 2) * V.SXY));
-        const int sbit = (bx & 3) | ((by & 3) << 2) | ((bz & 3) << 4);
-        s.brick = ((super >> sbit) & 1ull) ? __ldg(V.bricks + key) : 0ull;
-    }
+    const int key = (s.ix >> 2) + (s.iy >> 2) * V.BX + (s.iz >> 2) * V.BXY;
+    if (key != s.bkey) { s.bkey = key; s.brick = __ldg(V.bricks + key); }
     VT_TALLY(S, 1);
     const int bit = (s.ix & 3) | ((s.iy & 3) << 2) | ((s.iz & 3) << 4);
-    if ((s.brick >> bit) & 1ull) return DDA_HIT;                  // :44-50
+    if ((unsigned int)(s.brick >> bit) & 1u) return DDA_HIT;      // :44-50
     // :51 mask = step(dis.xyz, dis.yxy) * step(dis.xyz, dis.zzx)   (ties step several axes at once)
     const bool mx = !(s.dy < s.dx) && !(s.dz < s.dx);
     const bool my = !(s.dx < s.dy) && !(s.dz < s.dy);

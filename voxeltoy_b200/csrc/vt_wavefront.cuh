@@ -9,17 +9,19 @@
 // whose state lives in HBM/L2 as SoA float4 arrays; the integrator loop of pathTracer.fs:214-292 becomes a
 // sequence of kernels, each running full warps over a compacted queue of path ids:
 //
-//   wf_generate   pathTracer.fs:172-208   RNG offset, camera ray, slab test, primary DDA (coherent, traced inline);
-//                                         misses write their tone-mapped background sample, hits are queued
+//   wf_generate   pathTracer.fs:172-196   RNG offset, camera ray, slab test, DDA set-up (dda.h:16-34) of the primary ray
+//   wf_trace      dda.h:38-57             the DDA loop alone, for primary, shadow and bounce rays alike: persistent warps
+//                                         whose lanes refill themselves from a compact queue of 48-byte ray records as
+//                                         soon as their ray ends, so the loop stays >= kWfLiveMin/32 lanes wide although
+//                                         ray lengths differ by 100x
+//   wf_classify   :202-208, :214, :282-291 routes every traced path: surface hit with bounces left -> the shade queue of
+//                                         its material type (Lambert / metal / plastic / other: wf_shade does not diverge
+//                                         on the material switch), everything else -> the finish queue
 //   repeat max_bounces times:
 //     wf_shade    :216-279 (+ :248/:282-289 of the previous iteration) resolve the previous shadow ray, add the
 //                                         environment on a miss, build the hit frame, sample the light and the
-//                                         BSDF; emits one shadow ray and one bounce ray per surviving path
-//     wf_trace    dda.h:63-100            persistent warps, every lane refills itself from a global ray counter as
-//                                         soon as its ray ends, so the DDA loop stays >= kTraceMin/32 lanes wide;
-//                                         the epilogue sorts surviving paths into one queue per material type
-//                                         (Lambert / metal / plastic / other) so wf_shade does not diverge on the
-//                                         material switch, and finished paths into a "finish" queue
+//                                         BSDF; emits the DDA set-up of one shadow and one bounce ray per surviving path
+//     wf_trace, wf_classify
 //   wf_shade      (last)                  only the finish queue is populated: resolve, tone-map, write the sample
 //   wf_accumulate accumulation.fs:10-18   folds the P samples of every pixel into the running average in pass order
 //
@@ -31,27 +33,33 @@
 namespace vt {
 
 constexpr int kWfQueues = 5;          // 0 = finish, 1..3 = material type 0..2, 4 = other material types
-constexpr int kWfTraceMin = 24;       // leave the stepping loop when fewer lanes than this are tracing
-constexpr int kWfStepChunk = 8;       // DDA iterations between two votes
+constexpr int kWfLiveMin = 24;        // refill the warp when fewer lanes than this hold a ray
+constexpr int kWfStepChunk = 4;       // DDA iterations between two refill checks
+constexpr int kWfGrab = 128;          // rays a warp reserves per atomic on the hand-out counter
+
+enum { WF_RAY_SHADOW = 0, WF_RAY_BOUNCE = 1, WF_RAY_PRIMARY = 2 };
+enum { WF_HIT_VOXEL = 1, WF_HIT_GROUND = 2, WF_HIT_PRIMARY = 16 };    // hit.w flags (+ nanmask << 8)
 
 // counts block of one iteration (device memory, zeroed once per batch)
 struct WfCounts {
+    unsigned long long tq_rq;         // low 32 bits: paths in the trace list, high 32 bits: rays in the ray queue
     unsigned int sq[kWfQueues];       // entries in the shade queues
-    unsigned int tq;                  // entries in the trace queue (paths; 2 rays each)
     unsigned int work;                // ray hand-out counter of wf_trace
-    unsigned int pad;
 };
 
 struct WfState {
     float4* __restrict__ ray0;        // ray origin xyz, dir x      (the ray whose hit is shaded next)
     float4* __restrict__ ray1;        // dir y, dir z, bsdf pdf, bounces (int bits)
-    float4* __restrict__ shadow;      // shadow dir xyz, light target (int bits, -1 = environment)
     float4* __restrict__ rad0;        // radiance xyz, throughput x
     float4* __restrict__ rad1;        // throughput y z, pending x y
     float4* __restrict__ rad2;        // pending z, pending_nan (int bits), rng offset x y (int bits)
-    int4* __restrict__ hit;           // hit voxel ix iy iz, code: bit0 hit voxel, bit1 ground, bits 8..10 nanmask
+    int4* __restrict__ hit;           // hit voxel ix iy iz, flags WF_HIT_* | nanmask << 8
     int* __restrict__ vis;            // shadow ray result: 1 = light visible
     float4* __restrict__ samples;     // tone-mapped sample per path (P * n_items)
+    // ray queue: the DDA state after dda.h:16-34, 48 bytes per ray, 2 rays per path at most
+    int4* __restrict__ rq0;           // voxel ix iy iz, path id
+    float4* __restrict__ rq1;         // dis xyz, aux (int bits): light target (shadow) / unused
+    float4* __restrict__ rq2;         // |1/d| xyz, (int bits) sign bits 0..2 (1 = negative) | ray type << 4
     unsigned int* __restrict__ sq[kWfQueues];
     unsigned int* __restrict__ tq;
     int n_items;                      // paths per pass (tiles * 4096)
@@ -87,21 +95,85 @@ VT_DEV int wf_material_queue(const Volume& V, const Frame& F, int ix, int iy, in
     return (type >= 0 && type <= 2) ? 1 + type : 4;
 }
 
-// warp-aggregated append of `pid` to queue q (q < 0: nothing). All 32 lanes must call.
-VT_DEV void wf_enqueue(const WfState& S, WfCounts* __restrict__ cnt, int q, unsigned int pid)
+// flags of a finished traversal (dda.h:63-79)
+VT_DEV int wf_hit_flags(int status, const Dda& s)
+{
+    const bool ground = (status != DDA_HIT) && !(s.nanmask & 2) && (s.iy < 0);       // dda.h:75-78
+    return (status == DDA_HIT ? WF_HIT_VOXEL : (ground ? WF_HIT_GROUND : 0)) | (s.nanmask << 8);
+}
+// pathTracer.fs:134-153: is the sampled light visible, given the end of the shadow traversal
+VT_DEV int wf_light_visible(const Volume& V, int target, int status, const Dda& s)
+{
+    const int flags = wf_hit_flags(status, s);
+    if (target < 0) return (flags & 3) == 0;                                            // environment: nothing in the way
+    // emissive voxel: the traversal must end on exactly that voxel (a ground or NaN position never equals it)
+    return status == DDA_HIT && (flags >> 8) == 0 && (s.ix + s.iy * V.X + s.iz * V.X * V.Y) == target;
+}
+
+VT_DEV void wf_store_ray(const WfState& S, unsigned int slot, const Dda& s, unsigned int pid, int aux, int type)
+{
+    S.rq0[slot] = make_int4(s.ix, s.iy, s.iz, (int)pid);
+    S.rq1[slot] = make_float4(s.dx, s.dy, s.dz, i2f(aux));
+    S.rq2[slot] = make_float4(s.ex, s.ey, s.ez, i2f((s.sx < 0 ? 1 : 0) | (s.sy < 0 ? 2 : 0) | (s.sz < 0 ? 4 : 0) | (type << 4)));
+}
+
+// Block-aggregated queue appends. Same-address global atomics serialise in L2 at roughly one per clock, and a wavefront
+// step appends millions of entries, so every append is aggregated twice: lanes -> warp (ballot), warps -> CTA (shared-memory
+// atomics), and one global atomicAdd per CTA and counter. ALL threads of the CTA must call these (uniform trip counts).
+struct WfBlockCounters { unsigned int cnt[kWfQueues + 2]; unsigned int base[kWfQueues + 2]; };   // [0..4] shade queues, [5] trace list, [6] rays
+
+// append `pid` to shade queue q (q < 0: nothing)
+VT_DEV void wf_enqueue(const WfState& S, WfCounts* __restrict__ cnt, int q, unsigned int pid, WfBlockCounters& sm)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    if (threadIdx.x < kWfQueues) sm.cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    unsigned int woff = 0, rank = 0;
     #pragma unroll
     for (int k = 0; k < kWfQueues; ++k) {
         const unsigned m = __ballot_sync(full, q == k);
         if (m == 0u) continue;
-        const int leader = __ffs(m) - 1;
         unsigned base = 0;
-        if (lane == leader) base = atomicAdd(&cnt->sq[k], (unsigned)__popc(m));
-        base = __shfl_sync(full, base, leader);
-        if (q == k) S.sq[k][base + (unsigned)__popc(m & ((1u << lane) - 1u))] = pid;
+        if (lane == 0) base = atomicAdd(&sm.cnt[k], (unsigned)__popc(m));
+        base = __shfl_sync(full, base, 0);
+        if (q == k) { woff = base; rank = (unsigned)__popc(m & lt); }
     }
+    __syncthreads();
+    if (threadIdx.x < kWfQueues && sm.cnt[threadIdx.x] != 0u) sm.base[threadIdx.x] = atomicAdd(&cnt->sq[threadIdx.x], sm.cnt[threadIdx.x]);
+    __syncthreads();
+    #pragma unroll
+    for (int k = 0; k < kWfQueues; ++k)
+        if (q == k) S.sq[k][sm.base[k] + woff + rank] = pid;
+}
+
+// reserve one trace-list entry per thread with `traced` and one ray-queue slot per set predicate.
+// Returns the trace-list slot; slot_a / slot_b are valid where want_a / want_b.
+VT_DEV unsigned int wf_reserve_rays(WfCounts* __restrict__ cnt, bool traced, bool want_a, bool want_b, unsigned int& slot_a, unsigned int& slot_b,
+                                    WfBlockCounters& sm)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    if (threadIdx.x < 2) sm.cnt[kWfQueues + threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned mt = __ballot_sync(full, traced), ma = __ballot_sync(full, want_a), mb = __ballot_sync(full, want_b);
+    unsigned int wt = 0, wr = 0;
+    if (mt != 0u) {
+        if (lane == 0) { wt = atomicAdd(&sm.cnt[kWfQueues], (unsigned)__popc(mt)); wr = atomicAdd(&sm.cnt[kWfQueues + 1], (unsigned)(__popc(ma) + __popc(mb))); }
+        wt = __shfl_sync(full, wt, 0); wr = __shfl_sync(full, wr, 0);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && sm.cnt[kWfQueues] != 0u) {
+        const unsigned long long b = atomicAdd(&cnt->tq_rq, (unsigned long long)sm.cnt[kWfQueues] | ((unsigned long long)sm.cnt[kWfQueues + 1] << 32));
+        sm.base[kWfQueues] = (unsigned int)b; sm.base[kWfQueues + 1] = (unsigned int)(b >> 32);
+    }
+    __syncthreads();
+    const unsigned int rbase = sm.base[kWfQueues + 1] + wr;
+    slot_a = rbase + (unsigned)__popc(ma & lt);
+    slot_b = rbase + (unsigned)__popc(ma) + (unsigned)__popc(mb & lt);
+    return sm.base[kWfQueues] + wt + (unsigned)__popc(mt & lt);
 }
 
 template <bool COUNT>
@@ -126,96 +198,203 @@ VT_DEV void wf_flush_tally(const Tally<COUNT>& tl, Counters* __restrict__ counte
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// wf_generate: pathTracer.fs:172-208. grid = (n_items / 128, n_passes)
+// wf_generate: pathTracer.fs:172-196 + dda.h:16-34 of the primary ray. grid = (n_items / 256, n_passes)
 // ---------------------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, int pass0,
-                   WfCounts* __restrict__ cnt, int* __restrict__ primary, Counters* __restrict__ counters)
+                   WfCounts* __restrict__ cnt, WfCounts* __restrict__ cnext, int* __restrict__ primary, Counters* __restrict__ counters)
 {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     const int pass_local = blockIdx.y;
     const unsigned int pid = (unsigned)pass_local * (unsigned)S.n_items + (unsigned)item;
+    __shared__ WfBlockCounters sm;
     Tally<COUNT> tl; tl.clear();
-    int px, py, q = -1;
+    int px, py, q = -1, status = DDA_NOHIT;
+    bool traced = false;
+    Dda s;
+    s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.sx = s.sy = s.sz = 1; s.dx = s.dy = s.dz = s.ex = s.ey = s.ez = 0.f;
     if (item < S.n_items && wf_item_pixel(F, L, item, px, py)) {
         const int sample = L.first_sample + (pass0 + pass_local) * L.sample_stride;
         const f3 frag = mk3((float)px + 0.5f, (float)py + 0.5f, 0.55f);
         int2 rng = rng_offset(px, py, sample, F.noise_w, F.noise_h);               // :174
-        f3 ro, rd, hit;
+        f3 ro, rd;
         generate_ray<COUNT>(F, frag, rng, ro, rd, tl);                             // :179
         const float t = ray_aabb(ro, rd, V.bmin, V.bmax);                          // :183
-        int prim = -1;
-        bool hit_ground = false;
-        bool surface = false;
-        if (!(t < 0.0f)) surface = traverse<COUNT>(V, ro + t * rd, rd, hit, hit_ground, tl);   // :196-202
-        if (!surface) {
-            const f3 c = tonemap(background_color<COUNT>(F, rd, tl));              // :187-194, :202-208
-            S.samples[pid] = make_float4(c.x, c.y, c.z, 1.0f);
+        S.ray0[pid] = make_float4(ro.x, ro.y, ro.z, rd.x);
+        S.ray1[pid] = make_float4(rd.y, rd.z, 0.0f, i2f(0));
+        S.rad0[pid] = make_float4(0.f, 0.f, 0.f, 1.0f);
+        S.rad1[pid] = make_float4(1.0f, 1.0f, 0.f, 0.f);
+        S.rad2[pid] = make_float4(0.f, i2f(0), i2f(rng.x), i2f(rng.y));
+        if (t < 0.0f) {                                                            // :187-194 -> finish queue
+            S.hit[pid] = make_int4(0, 0, 0, WF_HIT_PRIMARY);
+            q = 0;
         } else {
-            prim = hit_code(V, hit, hit_ground);
-            if (!(0 < F.max_bounces)) {                                            // :214 never entered
-                const f3 c = tonemap(mk3(0.0f));
-                S.samples[pid] = make_float4(c.x, c.y, c.z, 1.0f);
-            } else {
-                const int nm = (hit.x != hit.x ? 1 : 0) | (hit.y != hit.y ? 2 : 0) | (hit.z != hit.z ? 4 : 0);
-                const int ix = f2i(hit.x), iy = f2i(hit.y), iz = f2i(hit.z);
-                S.ray0[pid] = make_float4(ro.x, ro.y, ro.z, rd.x);
-                S.ray1[pid] = make_float4(rd.y, rd.z, 0.0f, i2f(0));
-                S.rad0[pid] = make_float4(0.f, 0.f, 0.f, 1.0f);
-                S.rad1[pid] = make_float4(1.0f, 1.0f, 0.f, 0.f);
-                S.rad2[pid] = make_float4(0.f, i2f(0), i2f(rng.x), i2f(rng.y));
-                S.hit[pid] = make_int4(ix, iy, iz, (hit_ground ? 2 : 1) | (nm << 8));
-                q = wf_material_queue(V, F, ix, iy, iz);
+            status = dda_begin<COUNT>(V, ro + t * rd, rd, s, tl);                  // :196-202
+            traced = true;
+            if (status != DDA_RUNNING) S.hit[pid] = make_int4(s.ix, s.iy, s.iz, wf_hit_flags(status, s) | WF_HIT_PRIMARY);
+        }
+        if (primary != nullptr && pass0 + pass_local == L.n_passes - 1) primary[(size_t)px + (size_t)py * (size_t)F.W] = -1;
+    }
+    wf_enqueue(S, cnext, q, pid, sm);
+    unsigned int slot_a, slot_b;
+    const bool want = traced && status == DDA_RUNNING;
+    const unsigned int tslot = wf_reserve_rays(cnt, traced, want, false, slot_a, slot_b, sm);
+    if (traced) S.tq[tslot] = pid;
+    if (want) wf_store_ray(S, slot_a, s, pid, 0, WF_RAY_PRIMARY);
+    wf_flush_tally<COUNT>(tl, counters);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// wf_trace: the loop of dda.h:38-57 for every ray record of the queue. Persistent warps; a warp reserves kWfGrab
+// rays per atomic and its lanes refill from that range whenever fewer than kWfLiveMin of them hold a ray.
+// ---------------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(256)
+wf_trace_kernel(const Volume V, const WfState S, WfCounts* __restrict__ cnt, Counters* __restrict__ counters)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned int n_rays = (unsigned int)(cnt->tq_rq >> 32);
+    Tally<COUNT> tl; tl.clear();
+
+    bool have = false, exhausted = false;
+    unsigned int range_next = 0, range_end = 0;     // warp-uniform
+    unsigned int pid = 0;
+    int type = 0, status = DDA_NOHIT, aux = 0;
+    Dda s;
+    s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.steps = 0; s.bkey = -1; s.brick = 0ull;
+    s.dx = s.dy = s.dz = 0.f; s.ex = s.ey = s.ez = 0.f; s.sx = s.sy = s.sz = 1;
+
+    for (;;) {
+        // ---- refill idle lanes ---------------------------------------------------------------------------
+        const unsigned need = __ballot_sync(full, !have);
+        if (!exhausted && __popc(need) > 32 - kWfLiveMin) {
+            if (range_next >= range_end) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&cnt->work, (unsigned)kWfGrab);
+                base = __shfl_sync(full, base, 0);
+                range_next = base;
+                range_end = min(base + (unsigned)kWfGrab, n_rays);
+                if (base >= n_rays) { exhausted = true; range_end = range_next = 0; }
+            }
+            if (!have) {
+                const unsigned r = range_next + (unsigned)__popc(need & lt);
+                if (r < range_end) {
+                    const int4 a = S.rq0[r]; const float4 b = S.rq1[r], c = S.rq2[r];
+                    s.ix = a.x; s.iy = a.y; s.iz = a.z; pid = (unsigned)a.w;
+                    s.dx = b.x; s.dy = b.y; s.dz = b.z; aux = f2bits(b.w);
+                    s.ex = c.x; s.ey = c.y; s.ez = c.z;
+                    const int bits = f2bits(c.w);
+                    s.sx = (bits & 1) ? -1 : 1; s.sy = (bits & 2) ? -1 : 1; s.sz = (bits & 4) ? -1 : 1;
+                    type = bits >> 4;
+                    s.steps = 0; s.bkey = -1;
+                    status = DDA_RUNNING;
+                    have = true;
+                }
+            }
+            range_next = min(range_next + (unsigned)__popc(need), range_end);
+        }
+        if (__ballot_sync(full, have) == 0u) { if (exhausted) break; else continue; }
+        // ---- the hot loop ----------------------------------------------------------------------------------
+        #pragma unroll
+        for (int k = 0; k < kWfStepChunk; ++k)
+            if (have && status == DDA_RUNNING) status = dda_step<COUNT>(V, s, tl);
+        // ---- retire finished rays --------------------------------------------------------------------------
+        if (have && status != DDA_RUNNING) {
+            if (type == WF_RAY_SHADOW) S.vis[pid] = wf_light_visible(V, aux, status, s);
+            else S.hit[pid] = make_int4(s.ix, s.iy, s.iz, wf_hit_flags(status, s) | (type == WF_RAY_PRIMARY ? WF_HIT_PRIMARY : 0));
+            have = false;
+        }
+    }
+    wf_flush_tally<COUNT>(tl, counters);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// wf_classify: routes the paths traced in this iteration (pathTracer.fs:202-208, :214, :282-291)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wf_classify_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, int pass0,
+                   const WfCounts* __restrict__ cin, WfCounts* __restrict__ cnext, int* __restrict__ primary)
+{
+    __shared__ WfBlockCounters sm;
+    const unsigned int n = (unsigned int)cin->tq_rq;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int n_round = (n + 255u) & ~255u;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        int q = -1;
+        unsigned int pid = 0;
+        if (i < n) {
+            pid = S.tq[i];
+            const int4 h = S.hit[pid];
+            const bool surface = (h.w & 3) != 0;
+            const bool is_primary = (h.w & WF_HIT_PRIMARY) != 0;
+            const int bounces = is_primary ? -1 : f2bits(S.ray1[pid].w);
+            q = (surface && bounces + 1 < F.max_bounces) ? wf_material_queue(V, F, h.x, h.y, h.z) : 0;
+            if (is_primary && surface && primary != nullptr) {
+                const int pass_local = (int)(pid / (unsigned)S.n_items), item = (int)(pid - (unsigned)pass_local * (unsigned)S.n_items);
+                int px, py;
+                if (pass0 + pass_local == L.n_passes - 1 && wf_item_pixel(F, L, item, px, py))
+                    primary[(size_t)px + (size_t)py * (size_t)F.W] = hit_code(V, wf_hit_pos(h), (h.w & WF_HIT_GROUND) != 0);
             }
         }
-        if (primary != nullptr && pass0 + pass_local == L.n_passes - 1) primary[(size_t)px + (size_t)py * (size_t)F.W] = prim;
+        wf_enqueue(S, cnext, q, pid, sm);
     }
-    wf_enqueue(S, cnt, q, pid);
-    wf_flush_tally<COUNT>(tl, counters);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // wf_shade: one loop iteration of pathTracer.fs:214-292 up to (not including) the two traversals, preceded by
 // the tail of the previous iteration (shadow-ray result :134-164, environment on a miss :282-289, bounces++).
-// first = 1: the paths come from wf_generate (no pending light sample, primary hit).
+// Queue 0 holds the paths that end here; queues 1..4 the surface hits sorted by material type.
 // ---------------------------------------------------------------------------------------------------------
 template <bool COUNT>
 __global__ void __launch_bounds__(128)
-wf_shade_kernel(const Volume V, const Frame F, const WfState S, int first,
-                const WfCounts* __restrict__ cin, WfCounts* __restrict__ cout, Counters* __restrict__ counters)
+wf_shade_kernel(const Volume V, const Frame F, const WfState S, WfCounts* __restrict__ cnt, Counters* __restrict__ counters)
 {
-    const unsigned full = 0xffffffffu;
+    __shared__ WfBlockCounters sm;
     const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
     Tally<COUNT> tl; tl.clear();
-    // chunks of 32 entries, queue after queue
+    // chunks of 32 entries, queue after queue; a CTA takes warps_per_cta consecutive chunks per iteration
     unsigned int n_q[kWfQueues], chunks_before[kWfQueues + 1];
     chunks_before[0] = 0;
     #pragma unroll
-    for (int k = 0; k < kWfQueues; ++k) { n_q[k] = cin->sq[k]; chunks_before[k + 1] = chunks_before[k] + ((n_q[k] + 31u) >> 5); }
+    for (int k = 0; k < kWfQueues; ++k) { n_q[k] = cnt->sq[k]; chunks_before[k + 1] = chunks_before[k] + ((n_q[k] + 31u) >> 5); }
     const int sel_x = F.shared->sel_index[0], sel_y = F.shared->sel_index[1], sel_z = F.shared->sel_index[2];
 
-    for (unsigned int chunk = (unsigned)warp_global; chunk < chunks_before[kWfQueues]; chunk += (unsigned)n_warps) {
+    for (unsigned int chunk0 = blockIdx.x * warps_per_cta; chunk0 < chunks_before[kWfQueues]; chunk0 += gridDim.x * warps_per_cta) {
+        const unsigned int chunk = chunk0 + (threadIdx.x >> 5);
         unsigned int cb = 0, nq = n_q[0];
         const unsigned int* __restrict__ qp = S.sq[0];
         #pragma unroll
         for (int j = 1; j < kWfQueues; ++j) if (chunk >= chunks_before[j]) { cb = chunks_before[j]; nq = n_q[j]; qp = S.sq[j]; }
         const unsigned int idx = ((chunk - cb) << 5) + (unsigned)lane;
-        const bool valid = idx < nq;
+        const bool valid = chunk < chunks_before[kWfQueues] && idx < nq;
         bool continues = false;
         unsigned int pid = 0;
+        int st_a = DDA_NOHIT, st_b = DDA_NOHIT, target = -1;
+        Dda sa, sb;
+        sa.ix = sa.iy = sa.iz = 0; sa.nanmask = 0; sa.sx = sa.sy = sa.sz = 1; sa.dx = sa.dy = sa.dz = sa.ex = sa.ey = sa.ez = 0.f;
+        sb = sa;
         if (valid) {
             pid = qp[idx];
-            const float4 r0 = S.ray0[pid], r1 = S.ray1[pid], a0 = S.rad0[pid], a1 = S.rad1[pid], a2 = S.rad2[pid];
+            const float4 r0 = S.ray0[pid], r1 = S.ray1[pid], a0 = S.rad0[pid];
             const int4 h = S.hit[pid];
-            f3 ro = mk3(r0.x, r0.y, r0.z), rd = mk3(r0.w, r1.x, r1.y);
-            f3 radiance = mk3(a0.x, a0.y, a0.z), throughput = mk3(a0.w, a1.x, a1.y);
+            const f3 ro = mk3(r0.x, r0.y, r0.z), rd = mk3(r0.w, r1.x, r1.y);
+            f3 radiance = mk3(a0.x, a0.y, a0.z);
             int bounces = f2bits(r1.w);
-            int2 rng = make_int2(f2bits(a2.z), f2bits(a2.w));
+            const bool surface = (h.w & 3) != 0;
             bool finished = false;
-            if (!first) {
+            float4 a1 = make_float4(1.f, 1.f, 0.f, 0.f), a2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (h.w & WF_HIT_PRIMARY) {
+                if (!surface) {                                                    // :187-194, :202-208
+                    radiance = background_color<COUNT>(F, rd, tl);
+                    finished = true;
+                } else if (!(0 < F.max_bounces)) finished = true;                  // :214 never entered
+                if (!finished) { a1 = S.rad1[pid]; a2 = S.rad2[pid]; }
+            } else {
+                a1 = S.rad1[pid]; a2 = S.rad2[pid];
                 // pathTracer.fs:248 with the shadow-ray result of the previous iteration
                 if (S.vis[pid] != 0) {
                     radiance = radiance + mk3(a1.z, a1.w, a2.x);
@@ -227,7 +406,8 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, int first,
                     if (pn & 2) radiance.y = qn;
                     if (pn & 4) radiance.z = qn;
                 }
-                if ((h.w & 3) == 0) {                                              // :282-289 the bounce ray left the scene
+                if (!surface) {                                                    // :282-289 the bounce ray left the scene
+                    const f3 throughput = mk3(a0.w, a1.x, a1.y);
                     const f4 Lp = evaluate_env<COUNT>(F, rd, tl);
                     const float mis = power_heuristic(r1.z, Lp.w);
                     radiance = radiance + (throughput * xyz(Lp)) * mis;
@@ -238,6 +418,8 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, int first,
                 }
             }
             if (!finished) {
+                f3 throughput = mk3(a0.w, a1.x, a1.y);
+                int2 rng = make_int2(f2bits(a2.z), f2bits(a2.w));
                 const f3 hit = wf_hit_pos(h);
                 Basis hb;
                 voxel_to_world(V, hit, ro, rd, hb);                                // :221-223
@@ -264,10 +446,15 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, int first,
                     throughput = throughput * ((xyz(bf) * gabs(dot(wi, hb.normal))) / bf.w);   // :276
                     S.ray0[pid] = make_float4(hb.position.x, hb.position.y, hb.position.z, wi.x);   // :278-279
                     S.ray1[pid] = make_float4(wi.y, wi.z, bf.w, i2f(bounces));
-                    S.shadow[pid] = make_float4(ls.wl.x, ls.wl.y, ls.wl.z, i2f(ls.target));
                     S.rad0[pid] = make_float4(radiance.x, radiance.y, radiance.z, throughput.x);
                     S.rad1[pid] = make_float4(throughput.y, throughput.z, pending.x, pending.y);
                     S.rad2[pid] = make_float4(pending.z, i2f(pending_nan), i2f(rng.x), i2f(rng.y));
+                    // dda.h:16-34 of the shadow ray (:133) and of the bounce ray (:282)
+                    target = ls.target;
+                    st_a = dda_begin<COUNT>(V, hb.position, xyz(ls.wl), sa, tl);
+                    st_b = dda_begin<COUNT>(V, hb.position, wi, sb, tl);
+                    if (st_a != DDA_RUNNING) S.vis[pid] = wf_light_visible(V, target, st_a, sa);
+                    if (st_b != DDA_RUNNING) S.hit[pid] = make_int4(sb.ix, sb.iy, sb.iz, wf_hit_flags(st_b, sb));
                     continues = true;
                 }
             }
@@ -276,93 +463,13 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, int first,
                 S.samples[pid] = make_float4(c.x, c.y, c.z, 1.0f);
             }
         }
-        // surviving paths go to the trace queue (two rays each)
-        const unsigned m = __ballot_sync(full, continues);
-        if (m != 0u) {
-            const int leader = __ffs(m) - 1;
-            unsigned base = 0;
-            if (lane == leader) base = atomicAdd(&cout->tq, (unsigned)__popc(m));
-            base = __shfl_sync(full, base, leader);
-            if (continues) S.tq[base + (unsigned)__popc(m & ((1u << lane) - 1u))] = pid;
-        }
-    }
-    wf_flush_tally<COUNT>(tl, counters);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// wf_trace: the shadow ray (:133) and the bounce ray (:282) of every path in the trace queue.
-// ray r = 2 * slot + type (0 shadow, 1 bounce). Persistent warps; lanes refill from cnt->work.
-// ---------------------------------------------------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(256)
-wf_trace_kernel(const Volume V, const Frame F, const WfState S, WfCounts* __restrict__ cnt, WfCounts* __restrict__ cnext,
-                Counters* __restrict__ counters)
-{
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const unsigned int n_rays = 2u * cnt->tq;
-    Tally<COUNT> tl; tl.clear();
-
-    bool have = false, exhausted = false;
-    unsigned int pid = 0;
-    int type = 0, status = DDA_NOHIT, aux = 0;     // aux: light target (shadow) or bounce count (bounce)
-    Dda s;
-    s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.steps = 0; s.bkey = -1; s.brick = 0ull;
-    s.dx = s.dy = s.dz = 0.f; s.ex = s.ey = s.ez = 0.f; s.sx = s.sy = s.sz = 0;
-
-    for (;;) {
-        // ---- refill idle lanes -------------------------------------------------------------------
-        if (!exhausted) {
-            const unsigned need = __ballot_sync(full, !have);
-            if (need != 0u) {
-                const int leader = __ffs(need) - 1;
-                unsigned base = 0;
-                if (lane == leader) base = atomicAdd(&cnt->work, (unsigned)__popc(need));
-                base = __shfl_sync(full, base, leader);
-                if (base + (unsigned)__popc(need) >= n_rays) exhausted = true;      // warp-uniform
-                if (!have) {
-                    const unsigned r = base + (unsigned)__popc(need & lt);
-                    if (r < n_rays) {
-                        pid = S.tq[r >> 1];
-                        type = (int)(r & 1u);
-                        const float4 r0 = S.ray0[pid];
-                        f3 d;
-                        if (type == 0) { const float4 sh = S.shadow[pid]; d = mk3(sh.x, sh.y, sh.z); aux = f2bits(sh.w); }
-                        else { const float4 r1 = S.ray1[pid]; d = mk3(r0.w, r1.x, r1.y); aux = f2bits(r1.w); }
-                        status = dda_begin<COUNT>(V, mk3(r0.x, r0.y, r0.z), d, s, tl);
-                        have = true;
-                    }
-                }
-            }
-        }
-        // ---- the hot loop: step every tracing lane ---------------------------------------------------
-        {
-            unsigned live = __ballot_sync(full, have && status == DDA_RUNNING);
-            const int thresh = exhausted ? 1 : kWfTraceMin;
-            while (__popc(live) >= thresh) {
-                #pragma unroll 1
-                for (int k = 0; k < kWfStepChunk; ++k)
-                    if (have && status == DDA_RUNNING) status = dda_step<COUNT>(V, s, tl);
-                live = __ballot_sync(full, have && status == DDA_RUNNING);
-            }
-        }
-        // ---- retire finished rays -------------------------------------------------------------------------
-        int q = -1;
-        if (have && status != DDA_RUNNING) {
-            const bool ground = (status != DDA_HIT) && !(s.nanmask & 2) && (s.iy < 0);     // dda.h:75-78
-            const bool surface = (status == DDA_HIT) || ground;
-            if (type == 0) {
-                S.vis[pid] = light_occluded(V, aux, surface, dda_position(s)) ? 0 : 1;      // pathTracer.fs:134-153
-            } else {
-                S.hit[pid] = make_int4(s.ix, s.iy, s.iz, (status == DDA_HIT ? 1 : (ground ? 2 : 0)) | (s.nanmask << 8));
-                if (!surface || !(aux + 1 < F.max_bounces)) q = 0;                           // :282-289 / :214 -> finish
-                else q = wf_material_queue(V, F, s.ix, s.iy, s.iz);
-            }
-            have = false;
-        }
-        wf_enqueue(S, cnext, q, pid);
-        if (exhausted && __ballot_sync(full, have) == 0u) break;
+        // surviving paths: one trace-list entry, up to two ray records
+        unsigned int slot_a, slot_b;
+        const bool want_a = continues && st_a == DDA_RUNNING, want_b = continues && st_b == DDA_RUNNING;
+        const unsigned int tslot = wf_reserve_rays(cnt, continues, want_a, want_b, slot_a, slot_b, sm);
+        if (continues) S.tq[tslot] = pid;
+        if (want_a) wf_store_ray(S, slot_a, sa, pid, target, WF_RAY_SHADOW);
+        if (want_b) wf_store_ray(S, slot_b, sb, pid, 0, WF_RAY_BOUNCE);
     }
     wf_flush_tally<COUNT>(tl, counters);
 }
