@@ -193,6 +193,7 @@ def main():
     barrier()
     r.resetRender()
     launches0 = ctx.counters()["kernel_launches"]
+    ctx.kernel_timing_enable(True); ctx.kernel_times()             # cudaEvent pairs around every launch of the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -214,6 +215,7 @@ def main():
     t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.counters()["kernel_launches"] - launches0
+    ktimes = ctx.kernel_times(); ctx.kernel_timing_enable(False)
     ms_steps = sum(a.elapsed_time(b) for a, b in evs)
     ms_kernel = sum(a.elapsed_time(b) for a, b in kevs) / args.steps
     t = torch.tensor([ms_steps], dtype=torch.float64, device="cuda")
@@ -257,15 +259,23 @@ def main():
         r.renderPasses(PASSES)
     ctx.sync()
     cnt = ctx.counters(); ctx.counters_enable(False)
-    bps = bytes_per_sample(cnt, npx * PASSES * n_count)
-    bytes_per_launch = bps * npx * PASSES
-    achieved = bytes_per_launch / (ms_kernel * 1e-3) / 1e9
+    n_samp = float(npx * PASSES * n_count)
+    bps = bytes_per_sample(cnt, n_samp)
     peak, peak_src = measured_peak()
+    # dominant kernel: wf_trace (the DDA loop of dda.h:38-57). Algorithmic bytes = 4 B per DDA iteration (one
+    # 32-bit occupancy/offset word per step), counted by the kernel itself; duration = its launches inside the timed region.
+    trace_ms, trace_launches = ktimes["trace"]
+    steps_per_step = cnt["dda_steps"] / n_count                       # DDA iterations of one bench step (PASSES passes)
+    trace_bytes_per_launch = 4.0 * steps_per_step * args.steps / max(1, trace_launches)
+    trace_ms_per_launch = trace_ms / max(1, trace_launches)
+    achieved = trace_bytes_per_launch / (trace_ms_per_launch * 1e-3) / 1e9
+    step_achieved = bps * npx * PASSES / (ms_kernel * 1e-3) / 1e9     # every kernel of the step, all algorithmic bytes
+    kernel_ms_total = sum(v[0] for v in ktimes.values())
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("vt_render_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("wf_trace_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
 
@@ -281,12 +291,18 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "vt_render_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "wf_trace_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_sample": bps, "ms_per_launch": ms_kernel,
-                         "per_sample": {"S": cnt["dda_steps"] / (npx * PASSES * n_count), "R": cnt["rand_calls"] / (npx * PASSES * n_count),
-                                        "H": cnt["material_evals"] / (npx * PASSES * n_count), "E": cnt["cdf_loads"] / (npx * PASSES * n_count),
-                                        "Q": cnt["env_lookups"] / (npx * PASSES * n_count)}},
+                         "algorithmic_bytes_per_launch": trace_bytes_per_launch, "ms_per_launch": trace_ms_per_launch,
+                         "launches_per_step": trace_launches / float(args.steps),
+                         "share_of_step": trace_ms / kernel_ms_total if kernel_ms_total else None,
+                         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},
+                         "step": {"achieved": step_achieved, "frac": step_achieved / peak, "algorithmic_bytes_per_sample": bps,
+                                  "ms_per_step_device": ms_kernel},
+                         "per_sample": {"S": cnt["dda_steps"] / n_samp, "R": cnt["rand_calls"] / n_samp,
+                                        "H": cnt["material_evals"] / n_samp, "E": cnt["cdf_loads"] / n_samp,
+                                        "Q": cnt["env_lookups"] / n_samp},
+                         "note": "issue-bound, not bandwidth-bound: see profiles/ (issue slots busy, lanes per instruction)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -145,6 +145,13 @@ int vt_set_kernel_variant(vt_ctx* ctx, int variant);
 /* wavefront variant: upper bound on the paths (pixel-passes) in flight per batch; the passes of one vt_render call are
  * split into batches of floor(max_paths / pixels) passes (at least 1). Tuning knob, no effect on results. */
 int vt_set_wavefront_max_paths(vt_ctx* ctx, size_t max_paths);
+/* device time of the wavefront kernels by kind, measured with cudaEvent pairs around every launch on the context's
+ * stream while enabled; vt_get_kernel_times synchronises, returns the sums since the last call and clears them.
+ * (the reference's only timer is the per-frame GL_TIMESTAMP pair of timer/gpuTimer.cpp:33-69) */
+enum { VT_K_GENERATE = 0, VT_K_TRACE = 1, VT_K_CLASSIFY = 2, VT_K_SHADE = 3, VT_K_ACCUMULATE = 4, VT_K_COUNT = 5 };
+typedef struct vt_kernel_times { float ms[VT_K_COUNT]; uint32_t launches[VT_K_COUNT]; } vt_kernel_times;
+int vt_kernel_timing_enable(vt_ctx* ctx, int enable);
+int vt_get_kernel_times(vt_ctx* ctx, vt_kernel_times* out);
 int vt_counters_enable(vt_ctx* ctx, int enable);
 int vt_get_counters(vt_ctx* ctx, vt_counters* out);
 int vt_reset_counters(vt_ctx* ctx);

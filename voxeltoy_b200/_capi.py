@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvoxeltoy_b200.so")
+LIB_PATH = os.environ.get("VT_LIB_PATH") or os.path.join(_HERE, "libvoxeltoy_b200.so")   # VT_LIB_PATH: developer A/B builds
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)
@@ -68,6 +68,8 @@ SIGNATURES = {
     "vt_set_partition": (C.c_int, [P, C.c_int, C.c_int, C.c_int]),
     "vt_accum_device_ptr": (C.c_void_p, [P]),
     "vt_set_kernel_variant": (C.c_int, [P, C.c_int]),
+    "vt_kernel_timing_enable": (C.c_int, [P, C.c_int]),
+    "vt_get_kernel_times": (C.c_int, [P, C.c_void_p]),
     "vt_set_wavefront_max_paths": (C.c_int, [P, C.c_size_t]),
     "vt_counters_enable": (C.c_int, [P, C.c_int]),
     "vt_get_counters": (C.c_int, [P, C.POINTER(VtCounters)]),
@@ -280,6 +282,19 @@ class Context:
 
     def set_kernel_variant(self, variant):
         self._ck(self.lib.vt_set_kernel_variant(self.h, int(variant)))
+
+    KERNEL_KINDS = ("generate", "trace", "classify", "shade", "accumulate")
+
+    def kernel_timing_enable(self, on):
+        self._ck(self.lib.vt_kernel_timing_enable(self.h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{kind: (ms, launches)} of the wavefront kernels since the last call (device time, cudaEvent pairs)."""
+        class KT(C.Structure):
+            _fields_ = [("ms", C.c_float * 5), ("launches", C.c_uint32 * 5)]
+        kt = KT()
+        self._ck(self.lib.vt_get_kernel_times(self.h, C.byref(kt)))
+        return {k: (float(kt.ms[i]), int(kt.launches[i])) for i, k in enumerate(self.KERNEL_KINDS)}
 
     def set_wavefront_max_paths(self, n):
         self._ck(self.lib.vt_set_wavefront_max_paths(self.h, int(n)))

@@ -56,6 +56,10 @@ struct vt_ctx {
     WfState wf{}; void* d_wf_pool = nullptr; size_t wf_capacity = 0; size_t wf_max_paths = (size_t)8 << 20;
     WfCounts* d_wf_counts = nullptr; int wf_counts_cap = 0;
     int wf_shade_blocks[2] = {0, 0}, wf_trace_blocks[2] = {0, 0}, wf_sms = 0;
+    // per-kernel device timing (vt_kernel_timing_enable): event pairs around every wavefront launch
+    bool timing = false;
+    struct Timed { int kind; cudaEvent_t a, b; };
+    std::vector<Timed> timed; std::vector<cudaEvent_t> ev_pool;
     // counters
     Counters* d_counters = nullptr; bool count_enabled = false;
     uint64_t paths = 0, launches = 0;
@@ -149,6 +153,8 @@ void vt_destroy(vt_ctx* c)
     cudaFree(c->d_mat); cudaFree(c->d_bricks); cudaFree(c->d_supers); cudaFree(c->d_materials); cudaFree(c->d_emissive);
     cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum);
     cudaFree(c->d_wf_pool); cudaFree(c->d_wf_counts);
+    for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaFree(c->d_primary); cudaFree(c->d_work); cudaFree(c->d_shared); cudaFree(c->d_result); cudaFree(c->d_counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -463,6 +469,27 @@ int vt_set_wavefront_max_paths(vt_ctx* c, size_t n)
     c->wf_max_paths = n;
     return VT_OK;
 }
+int vt_kernel_timing_enable(vt_ctx* c, int enable)
+{
+    if (!c) return VT_ERR_INVALID;
+    c->timing = enable != 0;
+    return VT_OK;
+}
+int vt_get_kernel_times(vt_ctx* c, vt_kernel_times* out)
+{
+    if (!c || !out) return VT_ERR_INVALID;
+    VT_BIND(c);
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof *out);
+    for (auto& t : c->timed) {
+        float ms = 0.f;
+        VT_CUDA(c, cudaEventElapsedTime(&ms, t.a, t.b));
+        out->ms[t.kind] += ms; out->launches[t.kind] += 1;
+        c->ev_pool.push_back(t.a); c->ev_pool.push_back(t.b);
+    }
+    c->timed.clear();
+    return VT_OK;
+}
 int vt_enable_primary_hits(vt_ctx* c, int enable) { if (!c) return VT_ERR_INVALID; c->primary_enabled = enable != 0; return VT_OK; }
 int vt_counters_enable(vt_ctx* c, int enable) { if (!c) return VT_ERR_INVALID; c->count_enabled = enable != 0; return VT_OK; }
 
@@ -497,6 +524,13 @@ static int wf_reserve(vt_ctx* c, size_t n_paths, int n_iters)
     return VT_OK;
 }
 
+struct WfTimer {      // RAII event pair around one launch when timing is on
+    vt_ctx* c; int kind; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(vt_ctx* c) { if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
+    WfTimer(vt_ctx* c_, int kind_) : c(c_), kind(kind_) { if (c->timing) { a = get(c); b = get(c); cudaEventRecord(a, c->stream); } }
+    ~WfTimer() { if (a) { cudaEventRecord(b, c->stream); c->timed.push_back({kind, a, b}); } }
+};
+
 template <bool COUNT>
 static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLaunch& L, int my_tiles, int* prim)
 {
@@ -521,17 +555,18 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
     for (int pass0 = 0; pass0 < L.n_passes; pass0 += batch_max) {
         const int nb = std::min(batch_max, L.n_passes - pass0);
         VT_CUDA(c, cudaMemsetAsync(cn, 0, sizeof(WfCounts) * (size_t)n_iters, c->stream));
-        wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 256), (unsigned)nb), 256, 0, c->stream>>>(V, F, L, S, pass0, cn, cn + 1, prim, c->d_counters);
+        { WfTimer t(c, VT_K_GENERATE);
+          wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 256), (unsigned)nb), 256, 0, c->stream>>>(V, F, L, S, pass0, cn, cn + 1, prim, c->d_counters); }
         c->launches += 1;
         for (int it = 0; ; ++it) {
             // it == 0: primary rays; it >= 1: the shadow + bounce rays emitted by wf_shade(it)
-            wf_trace_kernel<COUNT><<<c->wf_trace_blocks[ci], 256, 0, c->stream>>>(V, S, cn + it, c->d_counters);
-            wf_classify_kernel<<<classify_blocks, 256, 0, c->stream>>>(V, F, L, S, pass0, cn + it, cn + it + 1, it == 0 ? prim : nullptr);
-            wf_shade_kernel<COUNT><<<c->wf_shade_blocks[ci], 128, 0, c->stream>>>(V, F, S, cn + it + 1, c->d_counters);
+            { WfTimer t(c, VT_K_TRACE); wf_trace_kernel<COUNT><<<c->wf_trace_blocks[ci], 256, 0, c->stream>>>(V, S, cn + it, c->d_counters); }
+            { WfTimer t(c, VT_K_CLASSIFY); wf_classify_kernel<<<classify_blocks, 256, 0, c->stream>>>(V, F, L, S, pass0, cn + it, cn + it + 1, it == 0 ? prim : nullptr); }
+            { WfTimer t(c, VT_K_SHADE); wf_shade_kernel<COUNT><<<c->wf_shade_blocks[ci], 128, 0, c->stream>>>(V, F, S, cn + it + 1, c->d_counters); }
             c->launches += 3;
             if (it == F.max_bounces) break;
         }
-        wf_accumulate_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, c->stream>>>(F, L, S, pass0, nb, c->d_accum);
+        { WfTimer t(c, VT_K_ACCUMULATE); wf_accumulate_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, c->stream>>>(F, L, S, pass0, nb, c->d_accum); }
         c->launches += 1;
     }
     return VT_OK;

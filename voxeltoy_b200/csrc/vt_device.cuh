@@ -92,8 +92,9 @@ VT_DEV f4 rng_next(const Frame& F, int2& off, Tally<COUNT>& tl)        // random
         const float4 t = __ldg(F.noise + ((size_t)off.x + (size_t)off.y * (size_t)F.noise_w));
         r = mk4(t.x, t.y, t.z, t.w);
     }
-    off.x = (off.x + 1) % F.noise_w;
-    if (off.x == 0) off.y = (off.y + 1) % F.noise_h;
+    // (x + 1) % w and (y + 1) % h for 0 <= x < w, 0 <= y < h (rng_offset and this function keep them there)
+    off.x = (off.x + 1 == F.noise_w) ? 0 : off.x + 1;
+    if (off.x == 0) off.y = (off.y + 1 == F.noise_h) ? 0 : off.y + 1;
     VT_TALLY(R, 1);
     return r;
 }
@@ -213,7 +214,8 @@ VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
     if (key != s.bkey) { s.bkey = key; s.brick = __ldg(V.bricks + key); }
     VT_TALLY(S, 1);
     const int bit = (s.ix & 3) | ((s.iy & 3) << 2) | ((s.iz & 3) << 4);
-    if ((unsigned int)(s.brick >> bit) & 1u) return DDA_HIT;      // :44-50
+    const unsigned int occ = (unsigned int)(s.brick >> bit);
+    if (occ & 1u) return DDA_HIT;                                 // :44-50
     // :51 mask = step(dis.xyz, dis.yxy) * step(dis.xyz, dis.zzx)   (ties step several axes at once)
     const bool mx = !(s.dy < s.dx) && !(s.dz < s.dx);
     const bool my = !(s.dx < s.dy) && !(s.dz < s.dy);

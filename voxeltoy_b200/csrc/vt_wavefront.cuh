@@ -33,7 +33,13 @@
 namespace vt {
 
 constexpr int kWfQueues = 5;          // 0 = finish, 1..3 = material type 0..2, 4 = other material types
-constexpr int kWfLiveMin = 24;        // refill the warp when fewer lanes than this hold a ray
+#ifndef VT_WF_LIVE_MIN
+#define VT_WF_LIVE_MIN 28
+#endif
+#ifndef VT_WF_SHADE_MIN_BLOCKS
+#define VT_WF_SHADE_MIN_BLOCKS 8
+#endif
+constexpr int kWfLiveMin = VT_WF_LIVE_MIN;        // refill the warp when fewer lanes than this hold a ray
 constexpr int kWfStepChunk = 4;       // DDA iterations between two refill checks
 constexpr int kWfGrab = 128;          // rays a warp reserves per atomic on the hand-out counter
 
@@ -349,7 +355,7 @@ wf_classify_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
 // Queue 0 holds the paths that end here; queues 1..4 the surface hits sorted by material type.
 // ---------------------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, VT_WF_SHADE_MIN_BLOCKS)
 wf_shade_kernel(const Volume V, const Frame F, const WfState S, WfCounts* __restrict__ cnt, Counters* __restrict__ counters)
 {
     __shared__ WfBlockCounters sm;
