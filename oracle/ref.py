@@ -1,0 +1,105 @@
+"""TEST INFRASTRUCTURE: ctypes binding of oracle/_ref/libvt_ref.so -- the reference's OWN GLSL programs
+(/root/reference/src/shaders) compiled for the CPU by oracle/shim/Makefile (glsl2cpp.py + glsl_emu.h + ref_glsl.cpp).
+
+Used (a) by tests/ to pin the C restatement oracle/vto.c against the real shader text, and (b) by bench.py's CPU arm
+(`cpu_baseline.kind = "reference"`, `--impl reference`). The library is built in this container, where /root/reference
+exists, and travels to the GPU box as a prebuilt file; nothing here reads /root/reference at run time.
+The product (voxeltoy_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import vto
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_ref", "libvt_ref.so")
+_LIB = None
+
+f32p, i32p = vto.f32p, vto.i32p
+
+
+def available():
+    return os.path.exists(_PATH)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(_PATH)
+        S = C.POINTER(vto.Scene)
+        L.vtref_describe.restype = C.c_char_p
+        L.vtref_render_pass.argtypes = [S, C.c_int, f32p, C.c_int]
+        L.vtref_preview_pass.argtypes = [S, C.c_int, f32p, C.c_int]
+        L.vtref_pick.argtypes = [S, C.c_float, C.c_float, C.c_float, f32p, i32p, f32p]
+        L.vtref_pick_focal.argtypes = [S, C.c_float, C.c_float]; L.vtref_pick_focal.restype = C.c_float
+        L.vtref_add_voxel.argtypes = [S, i32p, f32p, C.c_float, C.c_float, i32p]
+        L.vtref_remove_voxel.argtypes = [i32p, i32p]
+        L.vtref_voxelize.argtypes = [f32p, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t, f32p, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_uint8), C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def describe():
+    return lib().vtref_describe().decode()
+
+
+make_scene = vto.make_scene          # the same `vto_scene` struct feeds both implementations
+
+
+def _fp(a):
+    return a.ctypes.data_as(f32p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(i32p)
+
+
+def render_pass(scene, sample_count, n_threads=None):
+    """integrator/pathTracer.fs over the whole frame: (H, W, 4) float32, row 0 = bottom row."""
+    out = np.empty((scene.H, scene.W, 4), np.float32)
+    lib().vtref_render_pass(C.byref(scene), int(sample_count), _fp(out), int(n_threads or os.cpu_count() or 1))
+    return out
+
+
+def preview_pass(scene, sample_count, n_threads=None):
+    out = np.empty((scene.H, scene.W, 4), np.float32)
+    lib().vtref_preview_pass(C.byref(scene), int(sample_count), _fp(out), int(n_threads or os.cpu_count() or 1))
+    return out
+
+
+def pick(scene, px, py, near_z=0.1, prev_normal=(1.0, 0.0, 0.0, 0.0)):
+    index = np.zeros(4, np.int32); normal = np.zeros(4, np.float32)
+    pn = np.array(prev_normal, np.float32)
+    lib().vtref_pick(C.byref(scene), near_z, px, py, _fp(pn), _ip(index), _fp(normal))
+    return index, normal
+
+
+def pick_focal(scene, px, py):
+    return float(lib().vtref_pick_focal(C.byref(scene), px, py))
+
+
+def add_voxel(scene, sel_index, sel_normal, mx, my):
+    coord = np.zeros(3, np.int32)
+    si = np.ascontiguousarray(sel_index, np.int32); sn = np.ascontiguousarray(sel_normal, np.float32)
+    lib().vtref_add_voxel(C.byref(scene), _ip(si), _fp(sn), mx, my, _ip(coord))
+    return coord
+
+
+def remove_voxel(sel_index):
+    coord = np.zeros(3, np.int32)
+    si = np.ascontiguousarray(sel_index, np.int32)
+    lib().vtref_remove_voxel(_ip(si), _ip(coord))
+    return coord
+
+
+def voxelize(verts, idx, M, res, n_threads=None):
+    verts = np.ascontiguousarray(verts, np.float32); idx = np.ascontiguousarray(idx, np.uint32)
+    M = np.ascontiguousarray(M, np.float32)
+    X, Y, Z = [int(v) for v in res]
+    occ = np.zeros(X * Y * Z, np.uint8)
+    lib().vtref_voxelize(_fp(verts), verts.size // 3, idx.ctypes.data_as(C.POINTER(C.c_uint32)), idx.size, _fp(M), X, Y, Z,
+                         occ.ctypes.data_as(C.POINTER(C.c_uint8)), int(n_threads or os.cpu_count() or 1))
+    return occ

@@ -1,0 +1,108 @@
+"""Pins the CPU oracle (oracle/vto.c, a C restatement) against the reference's OWN GLSL programs compiled for the CPU
+(oracle/_ref/libvt_ref.so, built by oracle/shim/Makefile from /root/reference/src/shaders): same scene struct, same
+built-in arithmetic (oracle/vto_math.h), so every result must agree BIT FOR BIT. A mismatch means the restatement
+departed from the shader text (control flow, operand order, RNG consumption, tie handling ...).
+CPU only; the library is prebuilt where /root/reference is absent."""
+import numpy as np
+import pytest
+
+from oracle import ref
+from oracle import scene as oscene
+from oracle import vto
+from tests import util
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libvt_ref.so not built (needs /root/reference at build time)")
+
+
+def _same(a, b):
+    eq = util.same_bits(a, b)
+    assert eq.all(), "%d / %d floats differ, max |delta| = %g" % (int((~eq).sum()), eq.size, np.nanmax(np.abs(a - b)))
+
+
+def test_path_tracer_scene_fall_pinhole_gradient():
+    """BASELINE config 1 (reduced): scene_fall.vox, 1 bounce, pinhole, and 4 bounces from an orbited camera."""
+    vol = util.scene_fall_volume()
+    for d in (util.make_frame(vol, 128, 128, bounces=1, bg="grey"),
+              util.make_frame(vol, 160, 90, bounces=4, theta=120, phi=30),
+              util.make_frame(vol, 96, 64, bounces=0, theta=60, phi=20)):
+        s = vto.make_scene(d)
+        for k in (0, 1, 7):
+            _same(vto.render_pass(s, k, want_hits=False)[0], ref.render_pass(s, k))
+
+
+def test_path_tracer_ibl_thin_lens():
+    """BASELINE config 2's feature set: importance-sampled IBL (CDF search, bilinear lookup, rotation) + thin lens."""
+    from voxeltoy_b200 import scenes
+    env = oscene.build_env(scenes.synthetic_env(128, 64))
+    env["rotation"] = 0.7
+    d = util.make_frame(util.scene_fall_volume(), 128, 72, bounces=4, theta=120, phi=30, lens_model=1, fstop=2.8, env=env,
+                        focal_distance=650.0)
+    s = vto.make_scene(d)
+    for k in (0, 3):
+        _same(vto.render_pass(s, k, want_hits=False)[0], ref.render_pass(s, k))
+
+
+def test_path_tracer_mixed_materials_emissive_wireframe_selection():
+    """Lambert + metal + plastic + unknown type, emissive-voxel light sampling, wireframe overlay, selected voxel,
+    orthographic lens; NaNs from the unguarded microfacet terms must appear in the same pixels."""
+    vol = util.mixed_scene()
+    vol["materials"] = np.concatenate([vol["materials"], np.array([7.0, 0, 0, 0, 1, 1, 1, 0], np.float32)])   # a type-7 record
+    solid = np.flatnonzero(vol["grid"] >= 0)
+    vol["grid"] = vol["grid"].copy(); vol["grid"][solid[::97]] = len(vol["materials"]) - 8
+    n = vol["res"][0]
+    sel = (int(solid[5] % n), int((solid[5] // n) % n), int(solid[5] // (n * n)))
+    for kw in (dict(bounces=5, theta=115, phi=40), dict(bounces=3, theta=30, phi=60, wire_opacity=0.6, sel=sel),
+               dict(bounces=2, theta=200, phi=35, lens_model=2)):
+        d = util.make_frame(vol, 120, 96, **kw)
+        s = vto.make_scene(d)
+        a = vto.render_pass(s, 2, want_hits=False)[0]; b = ref.render_pass(s, 2)
+        _same(a, b)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+
+
+def test_edit_mode_preview():
+    d = util.make_frame(util.scene_fall_volume(), 128, 80, bounces=1, theta=100, phi=35, wire_opacity=0.5)
+    s = vto.make_scene(d)
+    _same(vto.preview_pass(s, 0), ref.preview_pass(s, 0))
+
+
+def test_services_pick_focal_add_remove():
+    vol = util.scene_fall_volume()
+    d = util.make_frame(vol, 200, 120, bounces=1, theta=120, phi=30)
+    s = vto.make_scene(d)
+    rng = np.random.RandomState(1)
+    for _ in range(60):
+        px, py = float(rng.uniform(0, 200)), float(rng.uniform(0, 120))
+        i0, n0 = vto.pick(s, px, py, near_z=d["near_z"]); i1, n1 = ref.pick(s, px, py, near_z=d["near_z"])
+        assert np.array_equal(i0, i1) and util.same_bits(n0, n1).all(), (px, py, i0, i1, n0, n1)
+        f0, f1 = vto.pick_focal(s, px, py), ref.pick_focal(s, px, py)
+        assert np.float32(f0).tobytes() == np.float32(f1).tobytes(), (px, py, f0, f1)
+        for mx, my in ((0.0, 0.0), (0.01, -0.002), (-0.003, 0.004), (0.0, -0.02)):
+            grid = vol["grid"].copy()
+            ok, c0 = vto.add_voxel(s, grid, i0, n0, mx, my)
+            c1 = ref.add_voxel(s, i1, n1, mx, my)
+            assert np.array_equal(c0, c1), (mx, my, c0, c1)
+        assert np.array_equal(ref.remove_voxel(i1), i1[:3])
+
+
+@pytest.mark.parametrize("res", [(32, 32, 32), (64, 64, 64), (96, 96, 96)])
+def test_voxelizer_bunny(res):
+    """shared/voxelize.{vs,gs} run per vertex / per triangle vs the oracle: identical occupancy sets."""
+    verts, idx = oscene.load_obj(util.BUNNY)
+    bmin, bmax = oscene.mesh_bounds(verts)
+    M = oscene.mesh_transform(bmin, bmax, res)
+    a = vto.voxelize(verts, idx, M, res); b = ref.voxelize(verts, idx, M, res)
+    assert a.sum() > 0 and np.array_equal(a, b), "%d voxels differ" % int((a != b).sum())
+
+
+def test_voxelizer_random_and_degenerate_triangles():
+    rng = np.random.RandomState(7)
+    verts = rng.uniform(0.05, 0.95, size=(300, 3)).astype(np.float32)
+    verts[10] = verts[11]                                  # degenerate triangles: repeated vertex, collinear points
+    verts[20] = (verts[21] + verts[22]) * np.float32(0.5)
+    verts[30:33] = np.float32([[0.25, 0.25, 0.5], [0.75, 0.25, 0.5], [0.25, 0.75, 0.5]])   # axis aligned, on voxel faces at 16^3
+    idx = np.arange(300, dtype=np.uint32)
+    M = np.eye(4, dtype=np.float32)
+    for res in ((16, 16, 16), (40, 40, 40)):
+        a = vto.voxelize(verts, idx, M, res); b = ref.voxelize(verts, idx, M, res)
+        assert np.array_equal(a, b), "%d voxels differ" % int((a != b).sum())
