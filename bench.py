@@ -167,8 +167,9 @@ def main():
     stream = torch.cuda.Stream()                  # a real (non-default) stream: handle 0 would mean "the context's own"
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    if world > 1:
-        r.setPartition(vt.VT_PART_SAMPLES, rank, world)
+    from voxeltoy_b200 import group as vtgroup
+    grp = vtgroup.RenderGroup(vtgroup.PART_SAMPLES, rank, world)        # sample partition: per-GPU work fixed (weak scaling)
+    grp.apply(r)
     vol = vt.host.load_vox(os.path.join(ROOT, "tests", "golden", "scene_fall.vox.gz"))     # host arrays for the e2e leg
 
     npx = W * H
@@ -178,9 +179,8 @@ def main():
     pinned_out = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
 
     def reduce_step():
-        if world > 1:
-            reduce_buf.copy_(accum)
-            dist.reduce(reduce_buf, dst=0)
+        if world > 1:      # NCCL SUM-reduce of the float4 accumulators to rank 0 + normalisation (voxeltoy_b200/group.py)
+            grp.combine(accum, max(1, ctx.num_samples()), dst=0, out=reduce_buf)
 
     def barrier():
         if world > 1:
