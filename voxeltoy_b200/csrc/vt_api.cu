@@ -501,18 +501,21 @@ static int wf_reserve(vt_ctx* c, size_t n_paths, int n_iters)
     if (n_paths > c->wf_capacity) {
         VT_CUDA(c, cudaStreamSynchronize(c->stream));
         cudaFree(c->d_wf_pool); c->d_wf_pool = nullptr; c->wf_capacity = 0;
-        // 7 x 16-byte path arrays, 2 x 48-byte ray records, vis, 6 queues: 236 bytes per path
-        const size_t bytes = n_paths * (7 * 16 + 2 * 48 + 4 + (kWfQueues + 1) * 4);
+        // per path: 2 generations x (5 x 16 B state + 16 B hit + vis + pid), sample, 2 x 48-byte ray records, 5 queues: 340 bytes
+        const size_t bytes = n_paths * (2 * (5 * 16 + 16 + 4 + 4) + 16 + 2 * 48 + kWfQueues * 4);
         VT_CUDA(c, cudaMalloc(&c->d_wf_pool, bytes));
         char* p = (char*)c->d_wf_pool;
         auto take = [&](size_t b) { char* r = p; p += b; return (void*)r; };
-        c->wf.ray0 = (float4*)take(n_paths * 16); c->wf.ray1 = (float4*)take(n_paths * 16);
-        c->wf.rad0 = (float4*)take(n_paths * 16); c->wf.rad1 = (float4*)take(n_paths * 16); c->wf.rad2 = (float4*)take(n_paths * 16);
-        c->wf.hit = (int4*)take(n_paths * 16); c->wf.samples = (float4*)take(n_paths * 16);
+        for (int g = 0; g < 2; ++g) {
+            WfBuf& B = c->wf.buf[g];
+            B.ray0 = (float4*)take(n_paths * 16); B.ray1 = (float4*)take(n_paths * 16);
+            B.rad0 = (float4*)take(n_paths * 16); B.rad1 = (float4*)take(n_paths * 16); B.rad2 = (float4*)take(n_paths * 16);
+            B.hit = (int4*)take(n_paths * 16);
+        }
+        c->wf.samples = (float4*)take(n_paths * 16);
         c->wf.rq0 = (int4*)take(n_paths * 32); c->wf.rq1 = (float4*)take(n_paths * 32); c->wf.rq2 = (float4*)take(n_paths * 32);
-        c->wf.vis = (int*)take(n_paths * 4);
+        for (int g = 0; g < 2; ++g) { c->wf.buf[g].vis = (int*)take(n_paths * 4); c->wf.buf[g].pid = (unsigned int*)take(n_paths * 4); }
         for (int k = 0; k < kWfQueues; ++k) c->wf.sq[k] = (unsigned int*)take(n_paths * 4);
-        c->wf.tq = (unsigned int*)take(n_paths * 4);
         c->wf_capacity = n_paths;
     }
     if (n_iters > c->wf_counts_cap) {
@@ -556,13 +559,15 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
         const int nb = std::min(batch_max, L.n_passes - pass0);
         VT_CUDA(c, cudaMemsetAsync(cn, 0, sizeof(WfCounts) * (size_t)n_iters, c->stream));
         { WfTimer t(c, VT_K_GENERATE);
-          wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 256), (unsigned)nb), 256, 0, c->stream>>>(V, F, L, S, pass0, cn, cn + 1, prim, c->d_counters); }
+          wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 256), (unsigned)nb), 256, 0, c->stream>>>(V, F, L, S, S.buf[0], pass0, cn, prim, c->d_counters); }
         c->launches += 1;
         for (int it = 0; ; ++it) {
             // it == 0: primary rays; it >= 1: the shadow + bounce rays emitted by wf_shade(it)
-            { WfTimer t(c, VT_K_TRACE); wf_trace_kernel<COUNT><<<c->wf_trace_blocks[ci], 256, 0, c->stream>>>(V, S, cn + it, c->d_counters); }
-            { WfTimer t(c, VT_K_CLASSIFY); wf_classify_kernel<<<classify_blocks, 256, 0, c->stream>>>(V, F, L, S, pass0, cn + it, cn + it + 1, it == 0 ? prim : nullptr); }
-            { WfTimer t(c, VT_K_SHADE); wf_shade_kernel<COUNT><<<c->wf_shade_blocks[ci], 128, 0, c->stream>>>(V, F, S, cn + it + 1, c->d_counters); }
+            // generation `it` lives in buf[it & 1]; wf_shade compacts its survivors into buf[(it + 1) & 1]
+            const WfBuf& cur = S.buf[it & 1]; const WfBuf& nxt = S.buf[(it + 1) & 1];
+            { WfTimer t(c, VT_K_TRACE); wf_trace_kernel<COUNT><<<c->wf_trace_blocks[ci], 256, 0, c->stream>>>(V, S, cur, cn + it, c->d_counters); }
+            { WfTimer t(c, VT_K_CLASSIFY); wf_classify_kernel<<<classify_blocks, 256, 0, c->stream>>>(V, F, L, S, cur, pass0, cn + it, cn + it + 1, it == 0 ? prim : nullptr); }
+            { WfTimer t(c, VT_K_SHADE); wf_shade_kernel<COUNT><<<c->wf_shade_blocks[ci], 128, 0, c->stream>>>(V, F, S, cur, nxt, cn + it + 1, c->d_counters); }
             c->launches += 3;
             if (it == F.max_bounces) break;
         }

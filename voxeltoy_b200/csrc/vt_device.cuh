@@ -189,7 +189,11 @@ VT_DEV int dda_begin(const Volume& V, f3 o, f3 d, Dda& s, Tally<COUNT>& tl)
     const f3 inc = mk3(1.0f) / d;                                 // :31
     const f3 sg = gsign(d);                                       // :32
     const f3 dis = (((vp - vo) + 0.5f) + sg * 0.5f) * inc;        // :34
-    if (vp.x != vp.x || vp.y != vp.y || vp.z != vp.z) {           // a NaN start voxel passes the bounds test of :24
+    // The stepping loop below drops the step cap of :38/:98: every iteration moves at least one coordinate by one voxel
+    // towards the outside (sign(d) = +-1 after the clamp of :29), so a ray leaves the grid within X+Y+Z iterations, and
+    // X+Y+Z <= sqrt(3) |res| < 2 ceil(|res|) = the cap. The exceptions -- a NaN start voxel (passes the bounds test of :24)
+    // or a NaN direction component (sign = 0, the ray may not move) -- take the literal loop with the cap.
+    if (vp.x != vp.x || vp.y != vp.y || vp.z != vp.z || d.x != d.x || d.y != d.y || d.z != d.z) {
         f3 hp;
         const bool isect = raymarch_slow<COUNT>(V, vp, dis, sg, inc, hp, tl);
         s.nanmask = (hp.x != hp.x ? 1 : 0) | (hp.y != hp.y ? 2 : 0) | (hp.z != hp.z ? 4 : 0);
@@ -223,7 +227,7 @@ VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
     if (mx) { s.dx = s.dx + s.ex; s.ix += s.sx; }                 // :52-53
     if (my) { s.dy = s.dy + s.ey; s.iy += s.sy; }
     if (mz) { s.dz = s.dz + s.ez; s.iz += s.sz; }
-    return (++s.steps < V.max_steps) ? DDA_RUNNING : DDA_NOHIT;   // :38,:55
+    return DDA_RUNNING;                                           // :38,:55 the cap cannot be reached here, see dda_begin
 }
 
 // dda.h:7-61 run to completion

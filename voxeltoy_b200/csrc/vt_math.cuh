@@ -34,13 +34,22 @@ VT_DEV f4 mk4(float x, float y, float z, float w) { f4 r; r.x = x; r.y = y; r.z 
 VT_DEV f4 mk4(f3 v, float w) { return mk4(v.x, v.y, v.z, w); }
 VT_DEV f3 xyz(f4 v) { return mk3(v.x, v.y, v.z); }
 
+// IEEE binary32 division with the zero numerator peeled off. div.rn's inline fast path rejects a == 0 (FCHK) and calls a
+// ~60-instruction subroutine; axis-aligned normals, black albedo channels and zero throughput make that the common case
+// in shading (10 % of wf_shade's instructions before this). 0 / b = (sign a ^ sign b) 0 for every b except 0 and NaN.
+VT_DEV float gdiv(float a, float b)
+{
+    if (a == 0.0f && b == b && b != 0.0f) return __int_as_float((__float_as_int(a) ^ __float_as_int(b)) & (int)0x80000000);
+    return a / b;
+}
+
 VT_DEV f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
 VT_DEV f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
 VT_DEV f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
-VT_DEV f3 operator/(f3 a, f3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
+VT_DEV f3 operator/(f3 a, f3 b) { return mk3(gdiv(a.x, b.x), gdiv(a.y, b.y), gdiv(a.z, b.z)); }
 VT_DEV f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 VT_DEV f3 operator*(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
-VT_DEV f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+VT_DEV f3 operator/(f3 a, float s) { return mk3(gdiv(a.x, s), gdiv(a.y, s), gdiv(a.z, s)); }
 VT_DEV f3 operator+(f3 a, float s) { return mk3(a.x + s, a.y + s, a.z + s); }
 VT_DEV f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
 

@@ -53,7 +53,10 @@ struct WfCounts {
     unsigned int work;                // ray hand-out counter of wf_trace
 };
 
-struct WfState {
+// Path state of one generation, SoA, indexed by a COMPACT slot: wf_shade reads generation g by slot and writes the surviving
+// paths to consecutive slots of generation g+1 (stream compaction of the state itself, not only of ids), so state traffic
+// is coalesced and every fetched sector is fully used. wf_trace writes hit / vis of the generation being traced.
+struct WfBuf {
     float4* __restrict__ ray0;        // ray origin xyz, dir x      (the ray whose hit is shaded next)
     float4* __restrict__ ray1;        // dir y, dir z, bsdf pdf, bounces (int bits)
     float4* __restrict__ rad0;        // radiance xyz, throughput x
@@ -61,13 +64,17 @@ struct WfState {
     float4* __restrict__ rad2;        // pending z, pending_nan (int bits), rng offset x y (int bits)
     int4* __restrict__ hit;           // hit voxel ix iy iz, flags WF_HIT_* | nanmask << 8
     int* __restrict__ vis;            // shadow ray result: 1 = light visible
-    float4* __restrict__ samples;     // tone-mapped sample per path (P * n_items)
+    unsigned int* __restrict__ pid;   // path id = pass_local * n_items + item (pixel)
+};
+
+struct WfState {
+    WfBuf buf[2];                     // generations alternate between the two
+    float4* __restrict__ samples;     // tone-mapped sample per path id (P * n_items)
     // ray queue: the DDA state after dda.h:16-34, 48 bytes per ray, 2 rays per path at most
-    int4* __restrict__ rq0;           // voxel ix iy iz, path id
+    int4* __restrict__ rq0;           // voxel ix iy iz, slot of the path in the generation being traced
     float4* __restrict__ rq1;         // dis xyz, aux (int bits): light target (shadow) / unused
     float4* __restrict__ rq2;         // |1/d| xyz, (int bits) sign bits 0..2 (1 = negative) | ray type << 4
-    unsigned int* __restrict__ sq[kWfQueues];
-    unsigned int* __restrict__ tq;
+    unsigned int* __restrict__ sq[kWfQueues];   // shade queues: slots of the generation just traced
     int n_items;                      // paths per pass (tiles * 4096)
 };
 
@@ -116,9 +123,10 @@ VT_DEV int wf_light_visible(const Volume& V, int target, int status, const Dda& 
     return status == DDA_HIT && (flags >> 8) == 0 && (s.ix + s.iy * V.X + s.iz * V.X * V.Y) == target;
 }
 
-VT_DEV void wf_store_ray(const WfState& S, unsigned int slot, const Dda& s, unsigned int pid, int aux, int type)
+VT_DEV void wf_store_ray(const WfState& S, unsigned int rslot, const Dda& s, unsigned int path_slot, int aux, int type)
 {
-    S.rq0[slot] = make_int4(s.ix, s.iy, s.iz, (int)pid);
+    const unsigned int slot = rslot;
+    S.rq0[slot] = make_int4(s.ix, s.iy, s.iz, (int)path_slot);
     S.rq1[slot] = make_float4(s.dx, s.dy, s.dz, i2f(aux));
     S.rq2[slot] = make_float4(s.ex, s.ey, s.ez, i2f((s.sx < 0 ? 1 : 0) | (s.sy < 0 ? 2 : 0) | (s.sz < 0 ? 4 : 0) | (type << 4)));
 }
@@ -128,8 +136,8 @@ VT_DEV void wf_store_ray(const WfState& S, unsigned int slot, const Dda& s, unsi
 // atomics), and one global atomicAdd per CTA and counter. ALL threads of the CTA must call these (uniform trip counts).
 struct WfBlockCounters { unsigned int cnt[kWfQueues + 2]; unsigned int base[kWfQueues + 2]; };   // [0..4] shade queues, [5] trace list, [6] rays
 
-// append `pid` to shade queue q (q < 0: nothing)
-VT_DEV void wf_enqueue(const WfState& S, WfCounts* __restrict__ cnt, int q, unsigned int pid, WfBlockCounters& sm)
+// append path slot `slot` to shade queue q (q < 0: nothing)
+VT_DEV void wf_enqueue(const WfState& S, WfCounts* __restrict__ cnt, int q, unsigned int slot, WfBlockCounters& sm)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -151,7 +159,7 @@ VT_DEV void wf_enqueue(const WfState& S, WfCounts* __restrict__ cnt, int q, unsi
     __syncthreads();
     #pragma unroll
     for (int k = 0; k < kWfQueues; ++k)
-        if (q == k) S.sq[k][sm.base[k] + woff + rank] = pid;
+        if (q == k) S.sq[k][sm.base[k] + woff + rank] = slot;
 }
 
 // reserve one trace-list entry per thread with `traced` and one ray-queue slot per set predicate.
@@ -204,50 +212,53 @@ VT_DEV void wf_flush_tally(const Tally<COUNT>& tl, Counters* __restrict__ counte
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// wf_generate: pathTracer.fs:172-196 + dda.h:16-34 of the primary ray. grid = (n_items / 256, n_passes)
+// wf_generate: pathTracer.fs:172-196 + dda.h:16-34 of the primary ray. grid = (n_items / 256, n_passes).
+// Every pixel of the frame gets a slot of generation 0; wf_classify routes the ones that miss the volume's box
+// to the finish queue.
 // ---------------------------------------------------------------------------------------------------------
 template <bool COUNT>
 __global__ void __launch_bounds__(256)
-wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, int pass0,
-                   WfCounts* __restrict__ cnt, WfCounts* __restrict__ cnext, int* __restrict__ primary, Counters* __restrict__ counters)
+wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, const WfBuf out, int pass0,
+                   WfCounts* __restrict__ cnt, int* __restrict__ primary, Counters* __restrict__ counters)
 {
+    __shared__ WfBlockCounters sm;
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     const int pass_local = blockIdx.y;
     const unsigned int pid = (unsigned)pass_local * (unsigned)S.n_items + (unsigned)item;
-    __shared__ WfBlockCounters sm;
     Tally<COUNT> tl; tl.clear();
-    int px, py, q = -1, status = DDA_NOHIT;
-    bool traced = false;
+    int px, py, status = DDA_NOHIT;
+    bool valid = false;
+    f3 ro = mk3(0.f), rd = mk3(0.f);
+    int2 rng = make_int2(0, 0);
+    int flags = WF_HIT_PRIMARY;
     Dda s;
     s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.sx = s.sy = s.sz = 1; s.dx = s.dy = s.dz = s.ex = s.ey = s.ez = 0.f;
     if (item < S.n_items && wf_item_pixel(F, L, item, px, py)) {
+        valid = true;
         const int sample = L.first_sample + (pass0 + pass_local) * L.sample_stride;
         const f3 frag = mk3((float)px + 0.5f, (float)py + 0.5f, 0.55f);
-        int2 rng = rng_offset(px, py, sample, F.noise_w, F.noise_h);               // :174
-        f3 ro, rd;
+        rng = rng_offset(px, py, sample, F.noise_w, F.noise_h);                    // :174
         generate_ray<COUNT>(F, frag, rng, ro, rd, tl);                             // :179
         const float t = ray_aabb(ro, rd, V.bmin, V.bmax);                          // :183
-        S.ray0[pid] = make_float4(ro.x, ro.y, ro.z, rd.x);
-        S.ray1[pid] = make_float4(rd.y, rd.z, 0.0f, i2f(0));
-        S.rad0[pid] = make_float4(0.f, 0.f, 0.f, 1.0f);
-        S.rad1[pid] = make_float4(1.0f, 1.0f, 0.f, 0.f);
-        S.rad2[pid] = make_float4(0.f, i2f(0), i2f(rng.x), i2f(rng.y));
-        if (t < 0.0f) {                                                            // :187-194 -> finish queue
-            S.hit[pid] = make_int4(0, 0, 0, WF_HIT_PRIMARY);
-            q = 0;
-        } else {
+        if (!(t < 0.0f)) {                                                         // else :187-194 -> finish queue
             status = dda_begin<COUNT>(V, ro + t * rd, rd, s, tl);                  // :196-202
-            traced = true;
-            if (status != DDA_RUNNING) S.hit[pid] = make_int4(s.ix, s.iy, s.iz, wf_hit_flags(status, s) | WF_HIT_PRIMARY);
+            if (status != DDA_RUNNING) flags = wf_hit_flags(status, s) | WF_HIT_PRIMARY;
         }
         if (primary != nullptr && pass0 + pass_local == L.n_passes - 1) primary[(size_t)px + (size_t)py * (size_t)F.W] = -1;
     }
-    wf_enqueue(S, cnext, q, pid, sm);
     unsigned int slot_a, slot_b;
-    const bool want = traced && status == DDA_RUNNING;
-    const unsigned int tslot = wf_reserve_rays(cnt, traced, want, false, slot_a, slot_b, sm);
-    if (traced) S.tq[tslot] = pid;
-    if (want) wf_store_ray(S, slot_a, s, pid, 0, WF_RAY_PRIMARY);
+    const bool want = valid && status == DDA_RUNNING;
+    const unsigned int slot = wf_reserve_rays(cnt, valid, want, false, slot_a, slot_b, sm);
+    if (valid) {
+        out.ray0[slot] = make_float4(ro.x, ro.y, ro.z, rd.x);
+        out.ray1[slot] = make_float4(rd.y, rd.z, 0.0f, i2f(0));
+        out.rad0[slot] = make_float4(0.f, 0.f, 0.f, 1.0f);
+        out.rad1[slot] = make_float4(1.0f, 1.0f, 0.f, 0.f);
+        out.rad2[slot] = make_float4(0.f, i2f(0), i2f(rng.x), i2f(rng.y));
+        out.pid[slot] = pid;
+        if (!want) out.hit[slot] = make_int4(s.ix, s.iy, s.iz, flags);
+    }
+    if (want) wf_store_ray(S, slot_a, s, slot, 0, WF_RAY_PRIMARY);
     wf_flush_tally<COUNT>(tl, counters);
 }
 
@@ -257,7 +268,7 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
 // ---------------------------------------------------------------------------------------------------------
 template <bool COUNT>
 __global__ void __launch_bounds__(256)
-wf_trace_kernel(const Volume V, const WfState S, WfCounts* __restrict__ cnt, Counters* __restrict__ counters)
+wf_trace_kernel(const Volume V, const WfState S, const WfBuf out, WfCounts* __restrict__ cnt, Counters* __restrict__ counters)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -267,8 +278,9 @@ wf_trace_kernel(const Volume V, const WfState S, WfCounts* __restrict__ cnt, Cou
 
     bool have = false, exhausted = false;
     unsigned int range_next = 0, range_end = 0;     // warp-uniform
-    unsigned int pid = 0;
-    int type = 0, status = DDA_NOHIT, aux = 0;
+    unsigned int pid = 0;                           // slot of the ray's path in `out`
+    int type = 0, status = DDA_NOHIT, aux = 0, chunks = 0;
+    const int chunk_guard = (V.X + V.Y + V.Z) / kWfStepChunk + 8;   // belt and braces: see dda_begin on why rays always leave
     Dda s;
     s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.steps = 0; s.bkey = -1; s.brick = 0ull;
     s.dx = s.dy = s.dz = 0.f; s.ex = s.ey = s.ez = 0.f; s.sx = s.sy = s.sz = 1;
@@ -297,6 +309,7 @@ wf_trace_kernel(const Volume V, const WfState S, WfCounts* __restrict__ cnt, Cou
                     type = bits >> 4;
                     s.steps = 0; s.bkey = -1;
                     status = DDA_RUNNING;
+                    chunks = 0;
                     have = true;
                 }
             }
@@ -307,10 +320,11 @@ wf_trace_kernel(const Volume V, const WfState S, WfCounts* __restrict__ cnt, Cou
         #pragma unroll
         for (int k = 0; k < kWfStepChunk; ++k)
             if (have && status == DDA_RUNNING) status = dda_step<COUNT>(V, s, tl);
+        if (++chunks > chunk_guard && status == DDA_RUNNING) status = DDA_NOHIT;
         // ---- retire finished rays --------------------------------------------------------------------------
         if (have && status != DDA_RUNNING) {
-            if (type == WF_RAY_SHADOW) S.vis[pid] = wf_light_visible(V, aux, status, s);
-            else S.hit[pid] = make_int4(s.ix, s.iy, s.iz, wf_hit_flags(status, s) | (type == WF_RAY_PRIMARY ? WF_HIT_PRIMARY : 0));
+            if (type == WF_RAY_SHADOW) out.vis[pid] = wf_light_visible(V, aux, status, s);
+            else out.hit[pid] = make_int4(s.ix, s.iy, s.iz, wf_hit_flags(status, s) | (type == WF_RAY_PRIMARY ? WF_HIT_PRIMARY : 0));
             have = false;
         }
     }
@@ -318,10 +332,11 @@ wf_trace_kernel(const Volume V, const WfState S, WfCounts* __restrict__ cnt, Cou
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// wf_classify: routes the paths traced in this iteration (pathTracer.fs:202-208, :214, :282-291)
+// wf_classify: routes the paths of the generation just traced (pathTracer.fs:202-208, :214, :282-291).
+// Sequential over the generation's slots: coalesced reads, one shade-queue entry (the slot) per path.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-wf_classify_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, int pass0,
+wf_classify_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, const WfBuf out, int pass0,
                    const WfCounts* __restrict__ cin, WfCounts* __restrict__ cnext, int* __restrict__ primary)
 {
     __shared__ WfBlockCounters sm;
@@ -330,22 +345,21 @@ wf_classify_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
     const unsigned int n_round = (n + 255u) & ~255u;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         int q = -1;
-        unsigned int pid = 0;
         if (i < n) {
-            pid = S.tq[i];
-            const int4 h = S.hit[pid];
+            const int4 h = out.hit[i];
             const bool surface = (h.w & 3) != 0;
             const bool is_primary = (h.w & WF_HIT_PRIMARY) != 0;
-            const int bounces = is_primary ? -1 : f2bits(S.ray1[pid].w);
+            const int bounces = is_primary ? -1 : f2bits(out.ray1[i].w);
             q = (surface && bounces + 1 < F.max_bounces) ? wf_material_queue(V, F, h.x, h.y, h.z) : 0;
             if (is_primary && surface && primary != nullptr) {
+                const unsigned int pid = out.pid[i];
                 const int pass_local = (int)(pid / (unsigned)S.n_items), item = (int)(pid - (unsigned)pass_local * (unsigned)S.n_items);
                 int px, py;
                 if (pass0 + pass_local == L.n_passes - 1 && wf_item_pixel(F, L, item, px, py))
                     primary[(size_t)px + (size_t)py * (size_t)F.W] = hit_code(V, wf_hit_pos(h), (h.w & WF_HIT_GROUND) != 0);
             }
         }
-        wf_enqueue(S, cnext, q, pid, sm);
+        wf_enqueue(S, cnext, q, i, sm);
     }
 }
 
@@ -356,7 +370,8 @@ wf_classify_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
 // ---------------------------------------------------------------------------------------------------------
 template <bool COUNT>
 __global__ void __launch_bounds__(128, VT_WF_SHADE_MIN_BLOCKS)
-wf_shade_kernel(const Volume V, const Frame F, const WfState S, WfCounts* __restrict__ cnt, Counters* __restrict__ counters)
+wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, const WfBuf out, WfCounts* __restrict__ cnt,
+                Counters* __restrict__ counters)
 {
     __shared__ WfBlockCounters sm;
     const int lane = threadIdx.x & 31;
@@ -380,13 +395,16 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, WfCounts* __rest
         bool continues = false;
         unsigned int pid = 0;
         int st_a = DDA_NOHIT, st_b = DDA_NOHIT, target = -1;
+        float4 o_ray0, o_ray1, o_rad0, o_rad1, o_rad2;
+        o_ray0 = o_ray1 = o_rad0 = o_rad1 = o_rad2 = make_float4(0.f, 0.f, 0.f, 0.f);
         Dda sa, sb;
         sa.ix = sa.iy = sa.iz = 0; sa.nanmask = 0; sa.sx = sa.sy = sa.sz = 1; sa.dx = sa.dy = sa.dz = sa.ex = sa.ey = sa.ez = 0.f;
         sb = sa;
         if (valid) {
-            pid = qp[idx];
-            const float4 r0 = S.ray0[pid], r1 = S.ray1[pid], a0 = S.rad0[pid];
-            const int4 h = S.hit[pid];
+            const unsigned int slot = qp[idx];
+            pid = in.pid[slot];
+            const float4 r0 = in.ray0[slot], r1 = in.ray1[slot], a0 = in.rad0[slot];
+            const int4 h = in.hit[slot];
             const f3 ro = mk3(r0.x, r0.y, r0.z), rd = mk3(r0.w, r1.x, r1.y);
             f3 radiance = mk3(a0.x, a0.y, a0.z);
             int bounces = f2bits(r1.w);
@@ -398,11 +416,11 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, WfCounts* __rest
                     radiance = background_color<COUNT>(F, rd, tl);
                     finished = true;
                 } else if (!(0 < F.max_bounces)) finished = true;                  // :214 never entered
-                if (!finished) { a1 = S.rad1[pid]; a2 = S.rad2[pid]; }
+                if (!finished) { a1 = in.rad1[slot]; a2 = in.rad2[slot]; }
             } else {
-                a1 = S.rad1[pid]; a2 = S.rad2[pid];
+                a1 = in.rad1[slot]; a2 = in.rad2[slot];
                 // pathTracer.fs:248 with the shadow-ray result of the previous iteration
-                if (S.vis[pid] != 0) {
+                if (in.vis[slot] != 0) {
                     radiance = radiance + mk3(a1.z, a1.w, a2.x);
                     VT_TALLY(H, 1);                                                // the BSDF evaluation of :161
                 } else {
@@ -450,17 +468,15 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, WfCounts* __rest
                     }
                     const f3 wi = local_to_world(lsWi, hb);                        // :273
                     throughput = throughput * ((xyz(bf) * gabs(dot(wi, hb.normal))) / bf.w);   // :276
-                    S.ray0[pid] = make_float4(hb.position.x, hb.position.y, hb.position.z, wi.x);   // :278-279
-                    S.ray1[pid] = make_float4(wi.y, wi.z, bf.w, i2f(bounces));
-                    S.rad0[pid] = make_float4(radiance.x, radiance.y, radiance.z, throughput.x);
-                    S.rad1[pid] = make_float4(throughput.y, throughput.z, pending.x, pending.y);
-                    S.rad2[pid] = make_float4(pending.z, i2f(pending_nan), i2f(rng.x), i2f(rng.y));
+                    o_ray0 = make_float4(hb.position.x, hb.position.y, hb.position.z, wi.x);   // :278-279
+                    o_ray1 = make_float4(wi.y, wi.z, bf.w, i2f(bounces));
+                    o_rad0 = make_float4(radiance.x, radiance.y, radiance.z, throughput.x);
+                    o_rad1 = make_float4(throughput.y, throughput.z, pending.x, pending.y);
+                    o_rad2 = make_float4(pending.z, i2f(pending_nan), i2f(rng.x), i2f(rng.y));
                     // dda.h:16-34 of the shadow ray (:133) and of the bounce ray (:282)
                     target = ls.target;
                     st_a = dda_begin<COUNT>(V, hb.position, xyz(ls.wl), sa, tl);
                     st_b = dda_begin<COUNT>(V, hb.position, wi, sb, tl);
-                    if (st_a != DDA_RUNNING) S.vis[pid] = wf_light_visible(V, target, st_a, sa);
-                    if (st_b != DDA_RUNNING) S.hit[pid] = make_int4(sb.ix, sb.iy, sb.iz, wf_hit_flags(st_b, sb));
                     continues = true;
                 }
             }
@@ -473,9 +489,14 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, WfCounts* __rest
         unsigned int slot_a, slot_b;
         const bool want_a = continues && st_a == DDA_RUNNING, want_b = continues && st_b == DDA_RUNNING;
         const unsigned int tslot = wf_reserve_rays(cnt, continues, want_a, want_b, slot_a, slot_b, sm);
-        if (continues) S.tq[tslot] = pid;
-        if (want_a) wf_store_ray(S, slot_a, sa, pid, target, WF_RAY_SHADOW);
-        if (want_b) wf_store_ray(S, slot_b, sb, pid, 0, WF_RAY_BOUNCE);
+        if (continues) {                     // the surviving path moves to slot `tslot` of the next generation
+            out.ray0[tslot] = o_ray0; out.ray1[tslot] = o_ray1; out.rad0[tslot] = o_rad0; out.rad1[tslot] = o_rad1; out.rad2[tslot] = o_rad2;
+            out.pid[tslot] = pid;
+            if (st_a != DDA_RUNNING) out.vis[tslot] = wf_light_visible(V, target, st_a, sa);
+            if (st_b != DDA_RUNNING) out.hit[tslot] = make_int4(sb.ix, sb.iy, sb.iz, wf_hit_flags(st_b, sb));
+        }
+        if (want_a) wf_store_ray(S, slot_a, sa, tslot, target, WF_RAY_SHADOW);
+        if (want_b) wf_store_ray(S, slot_b, sb, tslot, 0, WF_RAY_BOUNCE);
     }
     wf_flush_tally<COUNT>(tl, counters);
 }
