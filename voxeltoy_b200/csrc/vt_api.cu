@@ -25,10 +25,11 @@ struct vt_ctx {
     void* log_user = nullptr;
 
     // volume
-    int X = 0, Y = 0, Z = 0, BX = 0, BY = 0, BZ = 0, SX = 0, SY = 0, SZ = 0;
+    int X = 0, Y = 0, Z = 0, BX = 0, BY = 0, BZ = 0;     // voxel and brick counts; the brick array is padded by one brick per side
+    int PBX = 0, PBY = 0, PBZ = 0;                         // padded brick counts (strides)
     int32_t* d_mat = nullptr;
-    unsigned long long* d_bricks = nullptr;
-    unsigned long long* d_supers = nullptr;
+    unsigned long long* d_bricks_alloc = nullptr;         // padded array
+    unsigned long long* d_bricks = nullptr;               // brick (0,0,0): d_bricks_alloc + 1 + PBX + PBX*PBY
     float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0}, vsize[3] = {0, 0, 0};
     // scene arrays
     float* d_materials = nullptr; size_t n_materials = 0;
@@ -37,6 +38,7 @@ struct vt_ctx {
     float4* d_env = nullptr; int env_w = 0, env_h = 0;
     float* d_cdf_u = nullptr; int cdf_u_w = 0, cdf_u_h = 0;
     float* d_cdf_v = nullptr; int cdf_v_n = 0;
+    unsigned short* d_guide_v = nullptr; unsigned short* d_guide_u = nullptr; int guide_k = 0;
     float env_integral = 0.f;
     // frame
     vt_camera cam{};
@@ -150,8 +152,9 @@ void vt_destroy(vt_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_mat); cudaFree(c->d_bricks); cudaFree(c->d_supers); cudaFree(c->d_materials); cudaFree(c->d_emissive);
+    cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_materials); cudaFree(c->d_emissive);
     cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum);
+    cudaFree(c->d_guide_v); cudaFree(c->d_guide_u);
     cudaFree(c->d_wf_pool); cudaFree(c->d_wf_counts);
     for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -185,28 +188,37 @@ static int alloc_volume(vt_ctx* c, int X, int Y, int Z)
 {
     VT_REQ(c, X > 0 && Y > 0 && Z > 0 && X <= 2048 && Y <= 2048 && Z <= 2048, "volume resolution must be in [1, 2048]^3");
     if (X != c->X || Y != c->Y || Z != c->Z || !c->d_mat) {
-        cudaFree(c->d_mat); cudaFree(c->d_bricks); cudaFree(c->d_supers);
-        c->d_mat = nullptr; c->d_bricks = nullptr; c->d_supers = nullptr;
+        cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc);
+        c->d_mat = nullptr; c->d_bricks = nullptr; c->d_bricks_alloc = nullptr;
         c->X = X; c->Y = Y; c->Z = Z;
         c->BX = (X + 3) / 4; c->BY = (Y + 3) / 4; c->BZ = (Z + 3) / 4;
-        c->SX = (c->BX + 3) / 4; c->SY = (c->BY + 3) / 4; c->SZ = (c->BZ + 3) / 4;
+        c->PBX = c->BX + 2; c->PBY = c->BY + 2; c->PBZ = c->BZ + 2;
         VT_CUDA(c, cudaMalloc(&c->d_mat, sizeof(int32_t) * (size_t)X * Y * Z));
-        VT_CUDA(c, cudaMalloc(&c->d_bricks, sizeof(unsigned long long) * (size_t)c->BX * c->BY * c->BZ));
-        VT_CUDA(c, cudaMalloc(&c->d_supers, sizeof(unsigned long long) * (size_t)c->SX * c->SY * c->SZ));
+        VT_CUDA(c, cudaMalloc(&c->d_bricks_alloc, sizeof(unsigned long long) * (size_t)c->PBX * c->PBY * c->PBZ));
+        c->d_bricks = c->d_bricks_alloc + (1 + (size_t)c->PBX + (size_t)c->PBX * c->PBY);
     }
     volume_bounds(c);
     return VT_OK;
 }
 
+// empties the occupancy grid: zero everywhere inside the volume, the sentinel shell (every voxel of the padded brick array
+// that lies outside the volume) set -- see dda_step
+static int clear_occupancy(vt_ctx* c)
+{
+    const size_t npb = (size_t)c->PBX * c->PBY * c->PBZ;
+    VT_CUDA(c, cudaMemsetAsync(c->d_bricks_alloc, 0, npb * 8, c->stream));
+    vt_sentinel_kernel<<<grid_for(npb, 256), 256, 0, c->stream>>>(c->d_bricks_alloc, c->X, c->Y, c->Z, c->PBX, c->PBY, c->PBZ);
+    c->launches += 1;
+    return VT_OK;
+}
+
 static int rebuild_occupancy(vt_ctx* c)
 {
-    const size_t nb = (size_t)c->BX * c->BY * c->BZ, ns = (size_t)c->SX * c->SY * c->SZ;
-    VT_CUDA(c, cudaMemsetAsync(c->d_bricks, 0, nb * 8, c->stream));
-    VT_CUDA(c, cudaMemsetAsync(c->d_supers, 0, ns * 8, c->stream));
+    int rc = clear_occupancy(c);
+    if (rc != VT_OK) return rc;
     const size_t rows = (size_t)c->BX * c->Y * c->Z;
-    vt_build_bricks_kernel<<<grid_for(rows, 256), 256, 0, c->stream>>>(c->d_mat, c->d_bricks, c->X, c->Y, c->Z, c->BX, c->BX * c->BY);
-    vt_build_supers_kernel<<<grid_for(nb, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_supers, c->BX, c->BY, c->BZ, c->SX, c->SX * c->SY);
-    c->launches += 2;
+    vt_build_bricks_kernel<<<grid_for(rows, 256), 256, 0, c->stream>>>(c->d_mat, c->d_bricks, c->X, c->Y, c->Z, c->BX, c->PBX, c->PBX * c->PBY);
+    c->launches += 1;
     VT_CUDA(c, cudaGetLastError());
     return VT_OK;
 }
@@ -304,6 +316,23 @@ int vt_noise_upload(vt_ctx* c, const float* rgba, int w, int h)
     return upload_array(c, (void**)&c->d_noise, rgba, sizeof(float) * 4 * (size_t)w * h);
 }
 
+// guide table of one CDF search (csrc/vt_device.cuh cdf_search_guided): guide[j] = max({0} U {m in [1, n-2] : cdf[m] <= j/K}),
+// guide[K] = n - 2. Returns false when cdf[1..n-2] is not sorted (then the device keeps the literal bisection).
+static bool build_guide(const float* cdf, int n, int K, unsigned short* guide)
+{
+    if (n < 2 || n - 2 > 65535) return false;
+    for (int m = 2; m <= n - 2; ++m) if (!(cdf[m] >= cdf[m - 1])) return false;
+    if (n - 2 >= 1 && cdf[1] != cdf[1]) return false;
+    int r = 0;
+    for (int j = 0; j < K; ++j) {
+        const float t = (float)j / (float)K;
+        while (r + 1 <= n - 2 && cdf[r + 1] <= t) ++r;
+        guide[j] = (unsigned short)r;
+    }
+    guide[K] = (unsigned short)std::max(0, n - 2);
+    return true;
+}
+
 int vt_env_upload(vt_ctx* c, const float* rgb, int w, int h, const float* cdf_u, int cuw, int cuh,
                   const float* cdf_v, int cvn, float integral)
 {
@@ -320,6 +349,20 @@ int vt_env_upload(vt_ctx* c, const float* rgb, int w, int h, const float* cdf_u,
     if (rc == VT_OK) rc = upload_array(c, (void**)&c->d_cdf_v, cdf_v, sizeof(float) * (size_t)cvn);
     if (rc != VT_OK) return rc;
     c->env_w = w; c->env_h = h; c->cdf_u_w = cuw; c->cdf_u_h = cuh; c->cdf_v_n = cvn; c->env_integral = integral;
+    // guide tables for the two CDF searches (only when every row the search can reach exists and is sorted)
+    cudaFree(c->d_guide_v); cudaFree(c->d_guide_u); c->d_guide_v = nullptr; c->d_guide_u = nullptr; c->guide_k = 0;
+    const int K = 256, rows = cvn - 1;
+    if (rows >= 1 && cuh >= rows) {
+        std::vector<unsigned short> gv(K + 1), gu((size_t)rows * (K + 1));
+        bool ok = build_guide(cdf_v, cvn, K, gv.data());
+        for (int r = 0; ok && r < rows; ++r) ok = build_guide(cdf_u + (size_t)r * cuw, cuw, K, gu.data() + (size_t)r * (K + 1));
+        if (ok) {
+            rc = upload_array(c, (void**)&c->d_guide_v, gv.data(), gv.size() * sizeof(unsigned short));
+            if (rc == VT_OK) rc = upload_array(c, (void**)&c->d_guide_u, gu.data(), gu.size() * sizeof(unsigned short));
+            if (rc != VT_OK) return rc;
+            c->guide_k = K;
+        }
+    }
     return VT_OK;
 }
 
@@ -328,7 +371,8 @@ int vt_env_clear(vt_ctx* c)
     if (!c) return VT_ERR_INVALID;
     VT_BIND(c);
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v);
+    cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_guide_v); cudaFree(c->d_guide_u);
+    c->d_guide_v = nullptr; c->d_guide_u = nullptr; c->guide_k = 0;
     c->d_env = nullptr; c->d_cdf_u = nullptr; c->d_cdf_v = nullptr;
     c->env_w = c->env_h = c->cdf_u_w = c->cdf_u_h = c->cdf_v_n = 0; c->env_integral = 0.f;
     return VT_OK;
@@ -396,9 +440,9 @@ int vt_get_selection(vt_ctx* c, int32_t index[4], float normal[4])
 static Volume make_volume(const vt_ctx* c)
 {
     Volume V;
-    V.mat = c->d_mat; V.bricks = c->d_bricks; V.supers = c->d_supers;
+    V.mat = c->d_mat; V.bricks = c->d_bricks;
     V.X = c->X; V.Y = c->Y; V.Z = c->Z;
-    V.BX = c->BX; V.BXY = c->BX * c->BY; V.SX = c->SX; V.SXY = c->SX * c->SY;
+    V.BX = c->PBX; V.BXY = c->PBX * c->PBY;               // strides of the padded brick array
     V.bmin.x = c->bmin[0]; V.bmin.y = c->bmin[1]; V.bmin.z = c->bmin[2];
     V.bmax.x = c->bmax[0]; V.bmax.y = c->bmax[1]; V.bmax.z = c->bmax[2];
     V.vsize.x = c->vsize[0]; V.vsize.y = c->vsize[1]; V.vsize.z = c->vsize[2];
@@ -433,6 +477,7 @@ static Frame make_frame(const vt_ctx* c)
     F.env = c->d_env; F.env_w = c->env_w; F.env_h = c->env_h;
     F.cdf_u = c->d_cdf_u; F.cdf_u_w = c->cdf_u_w; F.cdf_u_h = c->cdf_u_h;
     F.cdf_v = c->d_cdf_v; F.cdf_v_n = c->cdf_v_n;
+    F.guide_v = c->d_guide_v; F.guide_u = c->d_guide_u; F.guide_k = c->guide_k;
     F.shared = c->d_shared;
     return F;
 }
@@ -694,20 +739,18 @@ int vt_voxelize(vt_ctx* c, const float* xyz, size_t n_verts, const uint32_t* ind
     VT_CUDA(c, cudaMemcpyAsync(d_xyz, xyz, n_verts * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     VT_CUDA(c, cudaMemcpyAsync(d_idx, indices, n_indices * sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));
     VT_CUDA(c, cudaMemcpyAsync(d_M, M, 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    const size_t nb = (size_t)c->BX * c->BY * c->BZ, ns = (size_t)c->SX * c->SY * c->SZ;
     const int n_tris = (int)(n_indices / 3);
     // timed region: clear + scatter + derive (kernel time incl. grid clear, excl. OBJ parse and H2D)
     VT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    VT_CUDA(c, cudaMemsetAsync(c->d_bricks, 0, nb * 8, c->stream));
-    VT_CUDA(c, cudaMemsetAsync(c->d_supers, 0, ns * 8, c->stream));
+    rc = clear_occupancy(c);
+    if (rc != VT_OK) return rc;
     if (n_tris > 0) {
         const int ctas = std::max(1, std::min((n_tris + 3) / 4, 148 * 16));
-        vt_voxelize_kernel<<<ctas, 128, 0, c->stream>>>(d_xyz, d_idx, n_tris, d_M, X, Y, Z, c->BX, c->BX * c->BY, c->d_bricks);
+        vt_voxelize_kernel<<<ctas, 128, 0, c->stream>>>(d_xyz, d_idx, n_tris, d_M, X, Y, Z, c->PBX, c->PBX * c->PBY, c->d_bricks);
         c->launches += 1;
     }
-    vt_build_supers_kernel<<<grid_for(nb, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_supers, c->BX, c->BY, c->BZ, c->SX, c->SX * c->SY);
-    vt_fill_offsets_kernel<<<grid_for((size_t)c->BX * Y * Z, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_mat, X, Y, Z, c->BX, c->BX * c->BY, fill);
-    c->launches += 2;
+    vt_fill_offsets_kernel<<<grid_for((size_t)c->BX * Y * Z, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_mat, X, Y, Z, c->BX, c->PBX, c->PBX * c->PBY, fill);
+    c->launches += 1;
     VT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     VT_CUDA(c, cudaGetLastError());
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -766,7 +809,7 @@ int vt_add_voxel(vt_ctx* c, float mx, float my)
     if (!c) return VT_ERR_INVALID;
     int rc = need_frame(c); if (rc) return rc;
     VT_BIND(c);
-    vt_add_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), make_frame(c), mx, my, c->d_shared, c->d_mat, c->d_bricks, c->d_supers, c->d_result);
+    vt_add_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), make_frame(c), mx, my, c->d_shared, c->d_mat, c->d_bricks, c->d_result);
     c->launches += 1;
     VT_CUDA(c, cudaGetLastError());
     return VT_OK;
@@ -775,7 +818,7 @@ int vt_remove_voxel(vt_ctx* c)
 {
     if (!c) return VT_ERR_INVALID;
     VT_BIND(c);
-    vt_remove_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), c->d_shared, c->d_mat, c->d_bricks, c->d_supers, c->d_result);
+    vt_remove_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), c->d_shared, c->d_mat, c->d_bricks, c->d_result);
     c->launches += 1;
     VT_CUDA(c, cudaGetLastError());
     return VT_OK;

@@ -10,20 +10,20 @@ namespace vt {
 // ----------------------------------------------------------------------------------
 // HBM layout of one scene (all pointers are device pointers owned by vt_ctx)
 // ----------------------------------------------------------------------------------
-// Occupancy is bit-packed in 4x4x4 bricks: one uint64 per brick, bit (x&3)|(y&3)<<2|(z&3)<<4,
-// bricks x-fastest. One level up, a "super" word per 4x4x4 bricks (16^3 voxels) holds one
-// bit per brick = "brick is not empty"; the DDA reads a brick word only when its super bit
-// is set, so traversal of empty space touches 1/4096 of the voxels' worth of memory and the
-// per-step arithmetic (identical to dda.h) runs out of registers.
+// Occupancy is bit-packed in 4x4x4 bricks: one uint64 per brick, bit (x&3)|(y&3)<<2|(z&3)<<4, bricks x-fastest.
+// The brick array is padded by one brick on every side and `bricks` points at brick (0,0,0), so brick coordinates -1 and
+// BX.. are addressable; every voxel of the padded array that lies outside the volume has its bit SET (sentinel shell,
+// vt_sentinel_kernel). A DDA step changes each coordinate by at most one, so a ray that leaves the volume "hits" the
+// shell in its next iteration: the stepping loop carries no bounds test, and the exit is told from a real hit after
+// the loop (dda_step). The DDA keeps a brick word in registers and touches memory only when the voxel moves to
+// another brick; the per-step arithmetic is identical to dda.h.
 // The int32 material-offset grid of the reference (R32I, x fastest, -1 empty) is kept as is
 // and read once per surface hit.
 struct Volume {
     const int32_t* __restrict__ mat;       // X*Y*Z material offsets
-    const unsigned long long* __restrict__ bricks;
-    const unsigned long long* __restrict__ supers;
+    const unsigned long long* __restrict__ bricks;   // brick (0,0,0) of the padded array
     int X, Y, Z;
-    int BX, BXY;                           // brick grid strides
-    int SX, SXY;                           // super grid strides
+    int BX, BXY;                           // strides of the padded brick array
     f3 bmin, bmax, vsize, resf;            // world bounds, wsVoxelSize, vec3(voxelResolution)
     f3 inv_extent;                         // 1.0 / (bmax - bmin)  (dda.h:16, hoisted: same IEEE divisions on the host)
     int max_steps;                         // dda.h:98
@@ -53,6 +53,10 @@ struct Frame {
     const float4* __restrict__ env; int env_w, env_h;       // rgb padded to float4
     const float* __restrict__ cdf_u; int cdf_u_w, cdf_u_h;
     const float* __restrict__ cdf_v; int cdf_v_n;
+    // guide tables of the two CDF searches (built by vt_env_upload when the CDFs are sorted; guide_k = 0: absent)
+    const unsigned short* __restrict__ guide_v;   // guide_k + 1 entries
+    const unsigned short* __restrict__ guide_u;   // (cdf_v_n - 1) rows x (guide_k + 1) entries
+    int guide_k;
     const Shared* __restrict__ shared;
 };
 
@@ -98,6 +102,9 @@ VT_DEV f4 rng_next(const Frame& F, int2& off, Tally<COUNT>& tl)        // random
     VT_TALLY(R, 1);
     return r;
 }
+
+// hint: bring the line holding p towards L1 (random 4-16 B gathers whose address is known long before the value is needed)
+VT_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
 // ----------------------------------------------------------------------------------
 // aabb.h:1-32
@@ -213,13 +220,17 @@ VT_DEV int dda_begin(const Volume& V, f3 o, f3 d, Dda& s, Tally<COUNT>& tl)
 template <bool COUNT>
 VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
 {
-    if ((unsigned)s.ix >= (unsigned)V.X || (unsigned)s.iy >= (unsigned)V.Y || (unsigned)s.iz >= (unsigned)V.Z) return DDA_NOHIT;   // :41-42
+    // :41-42 the bounds test is implied: outside the volume the occupancy bit is the sentinel (see Volume)
     const int key = (s.ix >> 2) + (s.iy >> 2) * V.BX + (s.iz >> 2) * V.BXY;
     if (key != s.bkey) { s.bkey = key; s.brick = __ldg(V.bricks + key); }
-    VT_TALLY(S, 1);
     const int bit = (s.ix & 3) | ((s.iy & 3) << 2) | ((s.iz & 3) << 4);
     const unsigned int occ = (unsigned int)(s.brick >> bit);
-    if (occ & 1u) return DDA_HIT;                                 // :44-50
+    if (occ & 1u) {                                               // :44-50, or the voxel is outside: :41-42
+        const bool inside = (unsigned)s.ix < (unsigned)V.X && (unsigned)s.iy < (unsigned)V.Y && (unsigned)s.iz < (unsigned)V.Z;
+        if (inside) VT_TALLY(S, 1);
+        return inside ? DDA_HIT : DDA_NOHIT;
+    }
+    VT_TALLY(S, 1);
     // :51 mask = step(dis.xyz, dis.yxy) * step(dis.xyz, dis.zzx)   (ties step several axes at once)
     const bool mx = !(s.dy < s.dx) && !(s.dz < s.dx);
     const bool my = !(s.dx < s.dy) && !(s.dz < s.dy);
@@ -236,7 +247,9 @@ VT_DEV bool raymarch(const Volume& V, f3 o, f3 d, f3& hit_pos, Tally<COUNT>& tl)
 {
     Dda s;
     int st = dda_begin<COUNT>(V, o, d, s, tl);
-    while (st == DDA_RUNNING) st = dda_step<COUNT>(V, s, tl);
+    int guard = V.X + V.Y + V.Z + 8;                              // never reached (dda_begin): belt and braces against a hang
+    while (st == DDA_RUNNING && --guard >= 0) st = dda_step<COUNT>(V, s, tl);
+    if (st == DDA_RUNNING) st = DDA_NOHIT;
     hit_pos = dda_position(s);
     return st == DDA_HIT;
 }
@@ -436,22 +449,43 @@ VT_DEV float cdf_v_at(const Frame& F, int i, Tally<COUNT>& tl)
     if ((unsigned)i >= (unsigned)F.cdf_v_n) return 0.0f;
     return __ldg(F.cdf_v + i);
 }
+// The searches of envMapSample.h:70-123 return R(s) = max({0} U {m in [1, n-2] : cdf[m] <= s}) whenever the CDF is sorted
+// (the probe order is then irrelevant). The guide table stores R(j / K) for j = 0..K-1 and n-2 for j = K, so for
+// s in [j/K, (j+1)/K) the answer lies in [guide[j], guide[j+1]] and the same bisection, started on that bracket, finds
+// it after 1-3 probes instead of 8-9 dependent L2-latency loads. K is a power of two: s * K and the bucket are exact.
+VT_DEV int cdf_search_guided(const float* __restrict__ cdf, const unsigned short* __restrict__ guide, int K, float s)
+{
+    const int j = min(K - 1, f2i(s * (float)K));
+    int lo = (int)__ldg(guide + j), hi = (int)__ldg(guide + j + 1) + 1;
+    while (lo != hi - 1) {
+        const int m = (lo + hi) >> 1;
+        if (s < __ldg(cdf + m)) hi = m; else lo = m;
+    }
+    return lo;
+}
 template <bool COUNT>
 VT_DEV f2 sample_env_texture(const Frame& F, float su, float sv, Tally<COUNT>& tl)   // envMapSample.h:23-123
 {
     const int sizeU = F.cdf_u_w, sizeV = F.cdf_v_n;
-    int lo = 0, hi = sizeV - 1;
-    while (lo != hi - 1) {                                        // :70-94
-        const int m = (lo + hi) / 2;
-        if (sv < cdf_v_at<COUNT>(F, m, tl)) hi = m; else lo = m;
+    int row, col;
+    // counting builds run the literal searches so that E equals the oracle's load count
+    if (!COUNT && F.guide_k > 0 && su >= 0.0f && su <= 1.0f && sv >= 0.0f && sv <= 1.0f) {
+        row = cdf_search_guided(F.cdf_v, F.guide_v, F.guide_k, sv);
+        col = cdf_search_guided(F.cdf_u + (size_t)row * F.cdf_u_w, F.guide_u + (size_t)row * (F.guide_k + 1), F.guide_k, su);
+    } else {
+        int lo = 0, hi = sizeV - 1;
+        while (lo != hi - 1) {                                        // :70-94
+            const int m = (lo + hi) / 2;
+            if (sv < cdf_v_at<COUNT>(F, m, tl)) hi = m; else lo = m;
+        }
+        row = lo;
+        lo = 0; hi = sizeU - 1;
+        while (lo != hi - 1) {                                        // :98-123
+            const int m = (lo + hi) / 2;
+            if (su < cdf_u_at<COUNT>(F, m, row, tl)) hi = m; else lo = m;
+        }
+        col = lo;
     }
-    const int row = lo;
-    lo = 0; hi = sizeU - 1;
-    while (lo != hi - 1) {                                        // :98-123
-        const int m = (lo + hi) / 2;
-        if (su < cdf_u_at<COUNT>(F, m, row, tl)) hi = m; else lo = m;
-    }
-    const int col = lo;
     float cl = cdf_u_at<COUNT>(F, col, row, tl), cu = cdf_u_at<COUNT>(F, col + 1, row, tl);   // :52-54
     const float du = (su - cl) / (cu - cl);
     cl = cdf_v_at<COUNT>(F, row, tl); cu = cdf_v_at<COUNT>(F, row + 1, tl);                    // :56-58

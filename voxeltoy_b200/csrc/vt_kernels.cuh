@@ -3,7 +3,7 @@
 //                                running-average accumulation (accumulation.fs)
 //   K5     vt_voxelize_kernel    warp-per-triangle THIN surface voxelization (voxelize.gs), atomicOr scatter
 //   K6-K9  vt_pick_kernel / vt_pick_focal_kernel / vt_add_voxel_kernel / vt_remove_voxel_kernel
-//   layout vt_build_bricks_kernel / vt_build_supers_kernel / vt_fill_offsets_kernel
+//   layout vt_build_bricks_kernel / vt_sentinel_kernel / vt_fill_offsets_kernel
 #pragma once
 #include "vt_device.cuh"
 
@@ -116,24 +116,17 @@ __global__ void vt_pick_focal_kernel(const Volume V, const Frame F, float px, fl
     sh->focal_distance = ray_aabb(ro, rd, vmin, vmax);
 }
 
-VT_DEV void set_voxel_bits(unsigned long long* bricks, unsigned long long* supers, const Volume& V, int x, int y, int z, bool on)
+VT_DEV void set_voxel_bits(unsigned long long* bricks, const Volume& V, int x, int y, int z, bool on)
 {
-    const int bx = x >> 2, by = y >> 2, bz = z >> 2;
-    const int key = bx + by * V.BX + bz * V.BXY;
+    const int key = (x >> 2) + (y >> 2) * V.BX + (z >> 2) * V.BXY;
     const unsigned long long bit = 1ull << ((x & 3) | ((y & 3) << 2) | ((z & 3) << 4));
-    unsigned long long b = bricks[key];
-    b = on ? (b | bit) : (b & ~bit);
-    bricks[key] = b;
-    const int sk = (bx >> 2) + (by >> 2) * V.SX + (bz >> 2) * V.SXY;
-    const unsigned long long sbit = 1ull << ((bx & 3) | ((by & 3) << 2) | ((bz & 3) << 4));
-    unsigned long long s = supers[sk];
-    s = (b != 0ull) ? (s | sbit) : (s & ~sbit);
-    supers[sk] = s;
+    const unsigned long long b = bricks[key];
+    bricks[key] = on ? (b | bit) : (b & ~bit);
 }
 
 // addVoxel.vs:16-41. result[0] = 1 if a voxel was written, result[1..3] = its coordinate.
 __global__ void vt_add_voxel_kernel(const Volume V, const Frame F, float mx, float my, const Shared* sh,
-                                    int* mat, unsigned long long* bricks, unsigned long long* supers, int* result)
+                                    int* mat, unsigned long long* bricks, int* result)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const f3 right = xyz(mul44(F.inv_mv, 1.0f, 0.0f, 0.0f, 0.0f));     // :18
@@ -157,20 +150,20 @@ __global__ void vt_add_voxel_kernel(const Volume V, const Frame F, float mx, flo
     int off = fetch_offset(V, sh->sel_index[0], sh->sel_index[1], sh->sel_index[2]);   // :37-40 (material of the selected voxel)
     if (off < 0) off = 0;
     mat[(size_t)cx + (size_t)cy * V.X + (size_t)cz * V.X * V.Y] = off;
-    set_voxel_bits(bricks, supers, V, cx, cy, cz, true);
+    set_voxel_bits(bricks, V, cx, cy, cz, true);
     result[0] = 1;
 }
 
 // removeVoxel.vs:8-11 (contract N2: the voxel becomes empty)
 __global__ void vt_remove_voxel_kernel(const Volume V, const Shared* sh,
-                                       int* mat, unsigned long long* bricks, unsigned long long* supers, int* result)
+                                       int* mat, unsigned long long* bricks, int* result)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int x = sh->sel_index[0], y = sh->sel_index[1], z = sh->sel_index[2];
     result[0] = 0; result[1] = x; result[2] = y; result[3] = z;
     if ((unsigned)x >= (unsigned)V.X || (unsigned)y >= (unsigned)V.Y || (unsigned)z >= (unsigned)V.Z) return;
     mat[(size_t)x + (size_t)y * V.X + (size_t)z * V.X * V.Y] = -1;
-    set_voxel_bits(bricks, supers, V, x, y, z, false);
+    set_voxel_bits(bricks, V, x, y, z, false);
     result[0] = 1;
 }
 
@@ -178,7 +171,7 @@ __global__ void vt_remove_voxel_kernel(const Volume V, const Shared* sh,
 // one thread per (brick, z-slice-of-4): builds 16 bits; a 4-thread group ORs them with shuffles.
 // Simpler and fast enough (upload-time only): one thread per brick row (4 voxels in x) -> atomicOr.
 __global__ void vt_build_bricks_kernel(const int* __restrict__ mat, unsigned long long* __restrict__ bricks,
-                                       int X, int Y, int Z, int BX, int BXY)
+                                       int X, int Y, int Z, int BX, int PBX, int BXY)
 {
     // thread -> (bx, y, z): reads up to 4 consecutive ints
     const size_t n = (size_t)BX * (size_t)Y * (size_t)Z;
@@ -194,29 +187,34 @@ __global__ void vt_build_bricks_kernel(const int* __restrict__ mat, unsigned lon
             if (x0 + k < X && __ldg(row + k) >= 0) m |= 1u << k;
         if (m) {
             const int sh = ((y & 3) << 2) | ((z & 3) << 4);
-            atomicOr(bricks + ((size_t)bx + (size_t)(y >> 2) * BX + (size_t)(z >> 2) * BXY), (unsigned long long)m << sh);
+            atomicOr(bricks + ((long long)bx + (long long)(y >> 2) * PBX + (long long)(z >> 2) * BXY), (unsigned long long)m << sh);
         }
     }
 }
 
-__global__ void vt_build_supers_kernel(const unsigned long long* __restrict__ bricks, unsigned long long* __restrict__ supers,
-                                       int BX, int BY, int BZ, int SX, int SXY)
+// sentinel shell: sets the bit of every voxel of the PADDED brick array that lies outside the volume (one thread per brick).
+// A DDA that leaves the volume lands on such a voxel in its very next iteration (a step changes each coordinate by at most 1),
+// so the stepping loop needs no bounds test of its own (dda_step).
+__global__ void vt_sentinel_kernel(unsigned long long* __restrict__ padded, int X, int Y, int Z, int PBX, int PBY, int PBZ)
 {
-    const size_t n = (size_t)BX * BY * BZ;
-    const int BXY = BX * BY;
+    const size_t n = (size_t)PBX * PBY * PBZ;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (__ldg(bricks + i) == 0ull) continue;
-        const int bz = (int)(i / BXY);
-        const int r = (int)(i - (size_t)bz * BXY);
-        const int by = r / BX, bx = r - by * BX;
-        const int sbit = (bx & 3) | ((by & 3) << 2) | ((bz & 3) << 4);
-        atomicOr(supers + ((size_t)(bx >> 2) + (size_t)(by >> 2) * SX + (size_t)(bz >> 2) * SXY), 1ull << sbit);
+        const int bx = (int)(i % PBX) - 1; const size_t r = i / PBX;
+        const int by = (int)(r % PBY) - 1, bz = (int)(r / PBY) - 1;
+        const int x0 = bx * 4, y0 = by * 4, z0 = bz * 4;
+        if (x0 >= 0 && x0 + 3 < X && y0 >= 0 && y0 + 3 < Y && z0 >= 0 && z0 + 3 < Z) continue;     // brick fully inside
+        unsigned long long m = 0ull;
+        for (int k = 0; k < 64; ++k) {
+            const int x = x0 + (k & 3), y = y0 + ((k >> 2) & 3), z = z0 + (k >> 4);
+            if ((unsigned)x >= (unsigned)X || (unsigned)y >= (unsigned)Y || (unsigned)z >= (unsigned)Z) m |= 1ull << k;
+        }
+        padded[i] |= m;
     }
 }
 
 // material-offset grid from occupancy: voxel = bit ? fill : -1. One thread per x-run of 4 voxels.
 __global__ void vt_fill_offsets_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
-                                       int X, int Y, int Z, int BX, int BXY, int fill)
+                                       int X, int Y, int Z, int BX, int PBX, int BXY, int fill)
 {
     const size_t n = (size_t)BX * (size_t)Y * (size_t)Z;
     const bool vec = (X & 3) == 0;
@@ -224,7 +222,7 @@ __global__ void vt_fill_offsets_kernel(const unsigned long long* __restrict__ br
         const int bx = (int)(i % BX);
         const size_t r = i / BX;
         const int y = (int)(r % Y), z = (int)(r / Y);
-        const unsigned long long b = __ldg(bricks + ((size_t)bx + (size_t)(y >> 2) * BX + (size_t)(z >> 2) * BXY));
+        const unsigned long long b = __ldg(bricks + ((long long)bx + (long long)(y >> 2) * PBX + (long long)(z >> 2) * BXY));
         const unsigned int m = (unsigned int)(b >> (((y & 3) << 2) | ((z & 3) << 4))) & 0xfu;
         int* row = mat + ((size_t)(bx << 2) + (size_t)y * X + (size_t)z * X * Y);
         if (vec) {

@@ -405,6 +405,13 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, 
             pid = in.pid[slot];
             const float4 r0 = in.ray0[slot], r1 = in.ray1[slot], a0 = in.rad0[slot];
             const int4 h = in.hit[slot];
+            {   // gathers whose addresses are known now but whose values are needed hundreds of instructions later
+                const float4 a2p = in.rad2[slot];
+                const int nx = f2bits(a2p.z), ny = f2bits(a2p.w);
+                if ((unsigned)nx < (unsigned)F.noise_w && (unsigned)ny < (unsigned)F.noise_h) prefetch_l1(F.noise + ((size_t)nx + (size_t)ny * (size_t)F.noise_w));
+                if ((unsigned)h.x < (unsigned)V.X && (unsigned)h.y < (unsigned)V.Y && (unsigned)h.z < (unsigned)V.Z)
+                    prefetch_l1(V.mat + ((size_t)h.x + (size_t)h.y * (size_t)V.X + (size_t)h.z * (size_t)V.X * (size_t)V.Y));
+            }
             const f3 ro = mk3(r0.x, r0.y, r0.z), rd = mk3(r0.w, r1.x, r1.y);
             f3 radiance = mk3(a0.x, a0.y, a0.z);
             int bounces = f2bits(r1.w);
