@@ -145,6 +145,9 @@ int vt_set_kernel_variant(vt_ctx* ctx, int variant);
 /* wavefront variant: upper bound on the paths (pixel-passes) in flight per batch; the passes of one vt_render call are
  * split into batches of floor(max_paths / pixels) passes (at least 1). Tuning knob, no effect on results. */
 int vt_set_wavefront_max_paths(vt_ctx* ctx, size_t max_paths);
+/* wavefront variant: number of batches in flight on internal streams (1..4, default 1). With 2 the ramp-down tail of one
+ * batch's kernels is filled by the next batch (+2-4 % throughput); accumulation stays in pass order. No effect on results. */
+int vt_set_wavefront_lanes(vt_ctx* ctx, int lanes);
 /* device time of the wavefront kernels by kind, measured with cudaEvent pairs around every launch on the context's
  * stream while enabled; vt_get_kernel_times synchronises, returns the sums since the last call and clears them.
  * (the reference's only timer is the per-frame GL_TIMESTAMP pair of timer/gpuTimer.cpp:33-69) */

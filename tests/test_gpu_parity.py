@@ -29,8 +29,9 @@ def _compare(ctx, d, n_passes=1, first=0, integrator=0):
         ref_hits = None
     # the wavefront renderer (variant 2, default; also with a path budget that splits the passes into several
     # batches), the one-thread-per-pixel megakernel (0) and the persistent path state machine (1) must produce the same bits
-    for variant, budget in ((0, 0), (1, 0), (2, 2 * 4096)):
+    for variant, budget, lanes in ((0, 0, 1), (1, 0, 1), (2, 2 * 4096, 1), (2, 4 * 4096, 2), (2, 0, 3)):
         ctx.set_kernel_variant(variant)
+        ctx.set_wavefront_lanes(lanes)
         if budget:
             ctx.set_wavefront_max_paths(budget)
         ctx.reset_accumulation()
@@ -38,7 +39,8 @@ def _compare(ctx, d, n_passes=1, first=0, integrator=0):
         got_v = ctx.read_average()
         hits_v = ctx.read_primary_hits()
         ctx.set_kernel_variant(2)
-        ctx.set_wavefront_max_paths(8 << 20)
+        ctx.set_wavefront_lanes(1)
+        ctx.set_wavefront_max_paths(32 << 20)
         assert util.same_bits(got, got_v).all() and np.array_equal(hits, hits_v), "kernel variant %d disagrees" % variant
     eq = util.same_bits(got, ref)
     bad = int((~eq).sum())

@@ -71,6 +71,7 @@ SIGNATURES = {
     "vt_kernel_timing_enable": (C.c_int, [P, C.c_int]),
     "vt_get_kernel_times": (C.c_int, [P, C.c_void_p]),
     "vt_set_wavefront_max_paths": (C.c_int, [P, C.c_size_t]),
+    "vt_set_wavefront_lanes": (C.c_int, [P, C.c_int]),
     "vt_counters_enable": (C.c_int, [P, C.c_int]),
     "vt_get_counters": (C.c_int, [P, C.POINTER(VtCounters)]),
     "vt_reset_counters": (C.c_int, [P]),
@@ -295,6 +296,9 @@ class Context:
         kt = KT()
         self._ck(self.lib.vt_get_kernel_times(self.h, C.byref(kt)))
         return {k: (float(kt.ms[i]), int(kt.launches[i])) for i, k in enumerate(self.KERNEL_KINDS)}
+
+    def set_wavefront_lanes(self, n):
+        self._ck(self.lib.vt_set_wavefront_lanes(self.h, int(n)))
 
     def set_wavefront_max_paths(self, n):
         self._ck(self.lib.vt_set_wavefront_max_paths(self.h, int(n)))

@@ -55,8 +55,15 @@ struct vt_ctx {
     // 2 = wavefront (vt_wavefront.cuh, default for the path tracer)
     int variant = 2; unsigned int* d_work = nullptr; int ps_blocks[2] = {0, 0};
     // wavefront state (variant 2): SoA path state + queues, sized for wf_capacity paths
-    WfState wf{}; void* d_wf_pool = nullptr; size_t wf_capacity = 0; size_t wf_max_paths = (size_t)8 << 20;
-    WfCounts* d_wf_counts = nullptr; int wf_counts_cap = 0;
+    // Batches run on up to kWfLanes internal streams ("lanes"), each with its own state pool, so the ramp-down tail of one
+    // batch's kernels is filled by the other's CTAs; accumulation stays on the caller's stream, in pass order.
+    static constexpr int kWfLanes = 4;
+    int wf_lanes = 1;      // default 1: kernels of one batch at a time (clean per-kernel timing); 2 overlaps batches, +2-4 %
+    WfState wf[kWfLanes]{}; void* d_wf_pool[kWfLanes] = {nullptr, nullptr, nullptr, nullptr}; size_t wf_capacity[kWfLanes] = {0, 0, 0, 0};
+    WfCounts* d_wf_counts[kWfLanes] = {nullptr, nullptr, nullptr, nullptr}; int wf_counts_cap[kWfLanes] = {0, 0, 0, 0};
+    cudaStream_t wf_stream[kWfLanes] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t wf_fork = nullptr, wf_done[kWfLanes] = {nullptr, nullptr, nullptr, nullptr}, wf_acc[kWfLanes] = {nullptr, nullptr, nullptr, nullptr};
+    size_t wf_max_paths = (size_t)32 << 20;
     int wf_shade_blocks[2] = {0, 0}, wf_trace_blocks[2] = {0, 0}, wf_sms = 0;
     // per-kernel device timing (vt_kernel_timing_enable): event pairs around every wavefront launch
     bool timing = false;
@@ -123,6 +130,7 @@ int vt_create(int device, vt_ctx** out)
     }
     c->stream = c->own_stream;
     if (const char* e = getenv("VT_WF_MAX_PATHS")) { const long long v = atoll(e); if (v > 0) c->wf_max_paths = (size_t)v; }   // tuning knob
+    if (const char* e = getenv("VT_WF_LANES")) { const int v = atoi(e); if (v >= 1 && v <= vt_ctx::kWfLanes) c->wf_lanes = v; }
     if (const char* e = getenv("VT_KERNEL_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->variant = v; }
     Shared sh;
     sh.focal_distance = 99999999.0f;                                  // renderer.cpp:712-720
@@ -155,7 +163,13 @@ void vt_destroy(vt_ctx* c)
     cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_materials); cudaFree(c->d_emissive);
     cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum);
     cudaFree(c->d_guide_v); cudaFree(c->d_guide_u);
-    cudaFree(c->d_wf_pool); cudaFree(c->d_wf_counts);
+    for (int k = 0; k < vt_ctx::kWfLanes; ++k) {
+        cudaFree(c->d_wf_pool[k]); cudaFree(c->d_wf_counts[k]);
+        if (c->wf_stream[k]) cudaStreamDestroy(c->wf_stream[k]);
+        if (c->wf_done[k]) cudaEventDestroy(c->wf_done[k]);
+        if (c->wf_acc[k]) cudaEventDestroy(c->wf_acc[k]);
+    }
+    if (c->wf_fork) cudaEventDestroy(c->wf_fork);
     for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaFree(c->d_primary); cudaFree(c->d_work); cudaFree(c->d_shared); cudaFree(c->d_result); cudaFree(c->d_counters);
@@ -535,48 +549,62 @@ int vt_get_kernel_times(vt_ctx* c, vt_kernel_times* out)
     c->timed.clear();
     return VT_OK;
 }
+int vt_set_wavefront_lanes(vt_ctx* c, int lanes)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, lanes >= 1 && lanes <= vt_ctx::kWfLanes, "lanes must be in [1, 4]");
+    c->wf_lanes = lanes;
+    return VT_OK;
+}
 int vt_enable_primary_hits(vt_ctx* c, int enable) { if (!c) return VT_ERR_INVALID; c->primary_enabled = enable != 0; return VT_OK; }
 int vt_counters_enable(vt_ctx* c, int enable) { if (!c) return VT_ERR_INVALID; c->count_enabled = enable != 0; return VT_OK; }
 
 } // extern "C" (the wavefront driver is a template)
 
 // ---- wavefront driver (variant 2, vt_wavefront.cuh) -------------------------------------------------------
-static int wf_reserve(vt_ctx* c, size_t n_paths, int n_iters)
+static int wf_reserve(vt_ctx* c, int lane, size_t n_paths, int n_iters)
 {
-    if (n_paths > c->wf_capacity) {
-        VT_CUDA(c, cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_wf_pool); c->d_wf_pool = nullptr; c->wf_capacity = 0;
+    if (!c->wf_stream[lane]) {
+        VT_CUDA(c, cudaStreamCreateWithFlags(&c->wf_stream[lane], cudaStreamNonBlocking));
+        VT_CUDA(c, cudaEventCreateWithFlags(&c->wf_done[lane], cudaEventDisableTiming));
+        VT_CUDA(c, cudaEventCreateWithFlags(&c->wf_acc[lane], cudaEventDisableTiming));
+        if (!c->wf_fork) VT_CUDA(c, cudaEventCreateWithFlags(&c->wf_fork, cudaEventDisableTiming));
+    }
+    if (n_paths > c->wf_capacity[lane]) {
+        VT_CUDA(c, cudaDeviceSynchronize());
+        cudaFree(c->d_wf_pool[lane]); c->d_wf_pool[lane] = nullptr; c->wf_capacity[lane] = 0;
         // per path: 2 generations x (5 x 16 B state + 16 B hit + vis + pid), sample, 2 x 48-byte ray records, 5 queues: 340 bytes
         const size_t bytes = n_paths * (2 * (5 * 16 + 16 + 4 + 4) + 16 + 2 * 48 + kWfQueues * 4);
-        VT_CUDA(c, cudaMalloc(&c->d_wf_pool, bytes));
-        char* p = (char*)c->d_wf_pool;
+        VT_CUDA(c, cudaMalloc(&c->d_wf_pool[lane], bytes));
+        char* p = (char*)c->d_wf_pool[lane];
         auto take = [&](size_t b) { char* r = p; p += b; return (void*)r; };
+        WfState& W = c->wf[lane];
         for (int g = 0; g < 2; ++g) {
-            WfBuf& B = c->wf.buf[g];
+            WfBuf& B = W.buf[g];
             B.ray0 = (float4*)take(n_paths * 16); B.ray1 = (float4*)take(n_paths * 16);
             B.rad0 = (float4*)take(n_paths * 16); B.rad1 = (float4*)take(n_paths * 16); B.rad2 = (float4*)take(n_paths * 16);
             B.hit = (int4*)take(n_paths * 16);
         }
-        c->wf.samples = (float4*)take(n_paths * 16);
-        c->wf.rq0 = (int4*)take(n_paths * 32); c->wf.rq1 = (float4*)take(n_paths * 32); c->wf.rq2 = (float4*)take(n_paths * 32);
-        for (int g = 0; g < 2; ++g) { c->wf.buf[g].vis = (int*)take(n_paths * 4); c->wf.buf[g].pid = (unsigned int*)take(n_paths * 4); }
-        for (int k = 0; k < kWfQueues; ++k) c->wf.sq[k] = (unsigned int*)take(n_paths * 4);
-        c->wf_capacity = n_paths;
+        W.samples = (float4*)take(n_paths * 16);
+        W.rq0 = (int4*)take(n_paths * 32); W.rq1 = (float4*)take(n_paths * 32); W.rq2 = (float4*)take(n_paths * 32);
+        for (int g = 0; g < 2; ++g) { W.buf[g].vis = (int*)take(n_paths * 4); W.buf[g].pid = (unsigned int*)take(n_paths * 4); }
+        for (int k = 0; k < kWfQueues; ++k) W.sq[k] = (unsigned int*)take(n_paths * 4);
+        c->wf_capacity[lane] = n_paths;
     }
-    if (n_iters > c->wf_counts_cap) {
-        VT_CUDA(c, cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_wf_counts); c->d_wf_counts = nullptr;
-        VT_CUDA(c, cudaMalloc(&c->d_wf_counts, sizeof(WfCounts) * (size_t)n_iters));
-        c->wf_counts_cap = n_iters;
+    if (n_iters > c->wf_counts_cap[lane]) {
+        VT_CUDA(c, cudaDeviceSynchronize());
+        cudaFree(c->d_wf_counts[lane]); c->d_wf_counts[lane] = nullptr;
+        VT_CUDA(c, cudaMalloc(&c->d_wf_counts[lane], sizeof(WfCounts) * (size_t)n_iters));
+        c->wf_counts_cap[lane] = n_iters;
     }
     return VT_OK;
 }
 
 struct WfTimer {      // RAII event pair around one launch when timing is on
-    vt_ctx* c; int kind; cudaEvent_t a = nullptr, b = nullptr;
+    vt_ctx* c; int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
     static cudaEvent_t get(vt_ctx* c) { if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
-    WfTimer(vt_ctx* c_, int kind_) : c(c_), kind(kind_) { if (c->timing) { a = get(c); b = get(c); cudaEventRecord(a, c->stream); } }
-    ~WfTimer() { if (a) { cudaEventRecord(b, c->stream); c->timed.push_back({kind, a, b}); } }
+    WfTimer(vt_ctx* c_, int kind_, cudaStream_t st_) : c(c_), kind(kind_), st(st_) { if (c->timing) { a = get(c); b = get(c); cudaEventRecord(a, st); } }
+    ~WfTimer() { if (a) { cudaEventRecord(b, st); c->timed.push_back({kind, a, b}); } }
 };
 
 template <bool COUNT>
@@ -593,30 +621,46 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
         c->wf_sms = std::max(1, sms);
     }
     const int n_items = my_tiles * kTile * kTile;
-    const int batch_max = (int)std::max<size_t>(1, c->wf_max_paths / (size_t)n_items);
+    // split the passes of this call into batches: at most wf_max_paths paths in flight over all lanes, and at least
+    // `lanes` batches when there are enough passes, so that two batches always overlap
+    const int lanes = std::max(1, std::min(c->wf_lanes, L.n_passes));
+    const int budget = (int)std::max<size_t>(1, c->wf_max_paths / (size_t)n_items / (size_t)lanes);
+    const int batch_max = std::max(1, std::min(budget, (L.n_passes + lanes - 1) / lanes));
     const int n_iters = F.max_bounces + 2;
-    int rc = wf_reserve(c, (size_t)n_items * (size_t)std::min(batch_max, L.n_passes), n_iters);
-    if (rc != VT_OK) return rc;
-    WfState S = c->wf; S.n_items = n_items;
-    WfCounts* cn = c->d_wf_counts;
+    for (int k = 0; k < lanes; ++k) {
+        const int rc = wf_reserve(c, k, (size_t)n_items * (size_t)batch_max, n_iters);
+        if (rc != VT_OK) return rc;
+    }
     const int classify_blocks = c->wf_sms * 8;
-    for (int pass0 = 0; pass0 < L.n_passes; pass0 += batch_max) {
+    VT_CUDA(c, cudaEventRecord(c->wf_fork, c->stream));
+    for (int k = 0; k < lanes; ++k) VT_CUDA(c, cudaStreamWaitEvent(c->wf_stream[k], c->wf_fork, 0));
+    int batch = 0;
+    for (int pass0 = 0; pass0 < L.n_passes; pass0 += batch_max, ++batch) {
+        const int lane = batch % lanes;
+        cudaStream_t st = c->wf_stream[lane];
+        WfState S = c->wf[lane]; S.n_items = n_items;
+        WfCounts* cn = c->d_wf_counts[lane];
         const int nb = std::min(batch_max, L.n_passes - pass0);
-        VT_CUDA(c, cudaMemsetAsync(cn, 0, sizeof(WfCounts) * (size_t)n_iters, c->stream));
-        { WfTimer t(c, VT_K_GENERATE);
-          wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 256), (unsigned)nb), 256, 0, c->stream>>>(V, F, L, S, S.buf[0], pass0, cn, prim, c->d_counters); }
+        if (batch >= lanes) VT_CUDA(c, cudaStreamWaitEvent(st, c->wf_acc[lane], 0));      // the lane's samples were folded in
+        VT_CUDA(c, cudaMemsetAsync(cn, 0, sizeof(WfCounts) * (size_t)n_iters, st));
+        { WfTimer t(c, VT_K_GENERATE, st);
+          wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 256), (unsigned)nb), 256, 0, st>>>(V, F, L, S, S.buf[0], pass0, cn, prim, c->d_counters); }
         c->launches += 1;
         for (int it = 0; ; ++it) {
             // it == 0: primary rays; it >= 1: the shadow + bounce rays emitted by wf_shade(it)
             // generation `it` lives in buf[it & 1]; wf_shade compacts its survivors into buf[(it + 1) & 1]
             const WfBuf& cur = S.buf[it & 1]; const WfBuf& nxt = S.buf[(it + 1) & 1];
-            { WfTimer t(c, VT_K_TRACE); wf_trace_kernel<COUNT><<<c->wf_trace_blocks[ci], 256, 0, c->stream>>>(V, S, cur, cn + it, c->d_counters); }
-            { WfTimer t(c, VT_K_CLASSIFY); wf_classify_kernel<<<classify_blocks, 256, 0, c->stream>>>(V, F, L, S, cur, pass0, cn + it, cn + it + 1, it == 0 ? prim : nullptr); }
-            { WfTimer t(c, VT_K_SHADE); wf_shade_kernel<COUNT><<<c->wf_shade_blocks[ci], 128, 0, c->stream>>>(V, F, S, cur, nxt, cn + it + 1, c->d_counters); }
+            { WfTimer t(c, VT_K_TRACE, st); wf_trace_kernel<COUNT><<<c->wf_trace_blocks[ci], 256, 0, st>>>(V, S, cur, cn + it, c->d_counters); }
+            { WfTimer t(c, VT_K_CLASSIFY, st); wf_classify_kernel<<<classify_blocks, 256, 0, st>>>(V, F, L, S, cur, pass0, cn + it, cn + it + 1, it == 0 ? prim : nullptr); }
+            { WfTimer t(c, VT_K_SHADE, st); wf_shade_kernel<COUNT><<<c->wf_shade_blocks[ci], 128, 0, st>>>(V, F, S, cur, nxt, cn + it + 1, c->d_counters); }
             c->launches += 3;
             if (it == F.max_bounces) break;
         }
-        { WfTimer t(c, VT_K_ACCUMULATE); wf_accumulate_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, c->stream>>>(F, L, S, pass0, nb, c->d_accum); }
+        // accumulation.fs in pass order: on the caller's stream, after this batch's last shade
+        VT_CUDA(c, cudaEventRecord(c->wf_done[lane], st));
+        VT_CUDA(c, cudaStreamWaitEvent(c->stream, c->wf_done[lane], 0));
+        { WfTimer t(c, VT_K_ACCUMULATE, c->stream); wf_accumulate_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, c->stream>>>(F, L, S, pass0, nb, c->d_accum); }
+        VT_CUDA(c, cudaEventRecord(c->wf_acc[lane], c->stream));
         c->launches += 1;
     }
     return VT_OK;
