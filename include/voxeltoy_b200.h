@@ -148,6 +148,9 @@ int vt_set_wavefront_max_paths(vt_ctx* ctx, size_t max_paths);
 /* wavefront variant: number of batches in flight on internal streams (1..4, default 1). With 2 the ramp-down tail of one
  * batch's kernels is filled by the next batch (+2-4 % throughput); accumulation stays in pass order. No effect on results. */
 int vt_set_wavefront_lanes(vt_ctx* ctx, int lanes);
+/* exact empty-space skip of the wavefront DDA (csrc/vt_device.cuh dda_skip): 0 off, 1 auto (default: volumes whose every
+ * side is >= 64 voxels), 2 always. Bit-identical results in every mode (the skipped steps' float additions are still done). */
+int vt_set_empty_skip(vt_ctx* ctx, int mode);
 /* device time of the wavefront kernels by kind, measured with cudaEvent pairs around every launch on the context's
  * stream while enabled; vt_get_kernel_times synchronises, returns the sums since the last call and clears them.
  * (the reference's only timer is the per-frame GL_TIMESTAMP pair of timer/gpuTimer.cpp:33-69) */
@@ -181,6 +184,10 @@ const char* vt_version(void);
 /* test hook: trace n rays (origin xyz, dir xyz interleaved, 6 floats each) through the current volume with
  * the DDA of dda.h:63-100; out_hit[4n] = (x,y,z, code) with code 1 voxel hit, 2 ground, 0 miss. */
 int vt_debug_trace_rays(vt_ctx* ctx, const float* rays, size_t n, float* out_hit);
+/* test hook: for each i, d[i] <- fl(d[i] + e[i]) while d[i] <= tau[i], at most nmax[i] times; k_out = additions done.
+ * literal = 1 runs the plain loop, 0 the closed form used by the empty-space skip (advance_until). Operands must be > 0. */
+int vt_debug_advance(vt_ctx* ctx, const float* d, const float* e, const float* tau, const int32_t* nmax, size_t n,
+                     float* d_out, int32_t* k_out, int literal);
 
 #ifdef __cplusplus
 }

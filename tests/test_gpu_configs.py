@@ -114,3 +114,62 @@ def test_c5_dense_noise_samples_and_edits(vt_ctx):
         vt_ctx.render(0, 1)
         ref1 = vto.render_pass(vto.make_scene(dict(d, grid=g)), 0, want_hits=False)[0]
         assert util.same_bits(vt_ctx.read_average(), ref1).all()
+
+
+def test_empty_space_skip_is_bit_identical(vt_ctx):
+    """The exact empty-space skip (dda_skip) forced on, on scenes with large empty regions, short rays, rays that graze
+    solid cells, a nearly empty volume and a dense one: every mode must reproduce the oracle's bits and primary hits."""
+    rng = np.random.RandomState(11)
+    t = scenes.MaterialTable()
+    t.lambert((0.7, 0.6, 0.5)); t.metal((0.9, 0.8, 0.6), 80.0); t.lambert((0.4, 0.4, 0.4), emission=(5.0, 4.0, 3.0))
+    cases = []
+    n = 96                                                    # a few small boxes floating in a big empty volume + a floor
+    ids = np.full((n, n, n), -1, np.int32); ids[:, :2, :] = 0
+    for _ in range(12):
+        c = rng.randint(4, n - 10, size=3); s = rng.randint(1, 7, size=3)
+        ids[c[0]:c[0] + s[0], c[1]:c[1] + s[1], c[2]:c[2] + s[2]] = rng.randint(0, 3)
+    cases.append(((n, n, n), ids.reshape(-1)))
+    ids = np.full((72, 130, 200), -1, np.int32); ids[5, 100, 17] = 1; ids[60, 3, 180] = 2      # [z, y, x]: non-cubic, almost empty
+    cases.append(((200, 130, 72), ids.reshape(-1)))
+    cases.append(((64, 64, 64), scenes.dense_noise_grid(64, density=0.02) % 3 * (scenes.dense_noise_grid(64, density=0.02) >= 0) - (scenes.dense_noise_grid(64, density=0.02) < 0)))
+    for res, idg in cases:
+        grid = scenes.ids_to_offsets(np.asarray(idg, np.int32), t.offsets); mats = t.array()
+        em = oscene.prune_interior_emissive(grid, res, scenes.emissive_list(grid, mats))
+        for kw in (dict(theta=130, phi=25), dict(theta=40, phi=70, lens_model=1, fstop=2.0, focal_distance=600.0), dict(theta=200, phi=5, distance=150.0)):
+            d = util.make_frame(dict(res=res, grid=grid, materials=mats, emissive=em), 160, 96, bounces=3, **kw)
+            s = vto.make_scene(d)
+            ref = vto.render_average(s, 2); ref_hits = vto.render_pass(s, 1)[1]
+            for mode in (2, 0, 1):
+                vt_ctx.set_empty_skip(mode)
+                util.upload(vt_ctx, d)
+                vt_ctx.enable_primary_hits(True)
+                vt_ctx.render(0, 2)
+                got = vt_ctx.read_average()
+                eq = util.same_bits(got, ref)
+                assert eq.all(), "skip mode %d, res %r, %r: %d floats differ" % (mode, res, kw, int((~eq).sum()))
+                assert np.array_equal(vt_ctx.read_primary_hits(), ref_hits)
+    vt_ctx.set_empty_skip(1)
+
+
+def test_advance_until_closed_form_equals_literal_loop(vt_ctx):
+    """advance_until (the O(binades) form of `while (d <= tau && k < nmax) d += e`) against the literal loop on the device,
+    on realistic DDA operands and on adversarial ones (exact ties, power-of-two increments, tiny/huge ratios, zero start)."""
+    rng = np.random.RandomState(5)
+    n = 400000
+    e = (10.0 ** rng.uniform(-3, 5, n)).astype(np.float32)
+    e[::11] = (e[::11].view(np.uint32) & np.uint32(0xFFFFF000)).view(np.float32)        # low bits zero: ties
+    e[::13] = (e[::13].view(np.uint32) & np.uint32(0xFF800000)).view(np.float32)        # powers of two
+    K = (10.0 ** rng.uniform(0, 3.3, n)).astype(np.float32)
+    d = ((rng.uniform(0, 1, n).astype(np.float32) + np.floor(K)) * e).astype(np.float32)
+    d[::7] = 0.0
+    d[::17] = (e[::17] * np.float32(2.0 ** 20)).astype(np.float32)                        # d >> e
+    nmax = rng.randint(1, 300, n).astype(np.int32)
+    steps = rng.randint(0, 320, n).astype(np.float32)
+    tau = ((d + steps * e) * rng.choice(np.float32([0.999, 1.0, 0.5, 1.001]), n)).astype(np.float32)
+    ok = (e > 0) & (tau > 0) & np.isfinite(tau)
+    d, e, tau, nmax = d[ok], e[ok], tau[ok], nmax[ok]
+    a_d, a_k = vt_ctx.debug_advance(d, e, tau, nmax, literal=True)
+    b_d, b_k = vt_ctx.debug_advance(d, e, tau, nmax, literal=False)
+    assert np.array_equal(a_k, b_k), "%d counts differ" % int((a_k != b_k).sum())
+    assert np.array_equal(a_d.view(np.uint32), b_d.view(np.uint32))
+    assert (a_k > 50).sum() > 10000 and (a_k == nmax).sum() > 1000 and (a_k == 0).sum() > 100

@@ -42,10 +42,14 @@ def c3():
     r.setRenderSettings(maxBounces=4)
     ctx = camera(r, 1920, 1080, 130, 25)
     r.renderPasses(2); ctx.sync()
+    ctx.kernel_timing_enable(True); ctx.kernel_times()
     dt = timed(r, ctx, 16)
+    kt = {k: round(v[0], 2) for k, v in ctx.kernel_times().items()}; ctx.kernel_timing_enable(False)
+    ctx.counters_enable(True); ctx.reset_counters(); r.renderPasses(1); cn = ctx.counters(); ctx.counters_enable(False)
     img = ctx.read_average()
     out = dict(config="C3 bunny 512^3 -> 1080p, 4 bounces, Lambert/metal/emissive", voxelize_ms=[ms1, ms2], solid=int((grid >= 0).sum()),
-               emissive=int(em.size), msamples_per_s=1920 * 1080 * 16 / dt / 1e6, nan_pixels=int(np.isnan(img).any(axis=2).sum()))
+               emissive=int(em.size), msamples_per_s=1920 * 1080 * 16 / dt / 1e6, kernel_ms=kt,
+               dda_steps_per_sample=cn["dda_steps"] / (1920 * 1080), nan_pixels=int(np.isnan(img).any(axis=2).sum()))
     r.close(); return out
 
 

@@ -72,6 +72,8 @@ SIGNATURES = {
     "vt_get_kernel_times": (C.c_int, [P, C.c_void_p]),
     "vt_set_wavefront_max_paths": (C.c_int, [P, C.c_size_t]),
     "vt_set_wavefront_lanes": (C.c_int, [P, C.c_int]),
+    "vt_set_empty_skip": (C.c_int, [P, C.c_int]),
+    "vt_debug_advance": (C.c_int, [P, f32p, f32p, f32p, i32p, C.c_size_t, f32p, i32p, C.c_int]),
     "vt_counters_enable": (C.c_int, [P, C.c_int]),
     "vt_get_counters": (C.c_int, [P, C.POINTER(VtCounters)]),
     "vt_reset_counters": (C.c_int, [P]),
@@ -296,6 +298,16 @@ class Context:
         kt = KT()
         self._ck(self.lib.vt_get_kernel_times(self.h, C.byref(kt)))
         return {k: (float(kt.ms[i]), int(kt.launches[i])) for i, k in enumerate(self.KERNEL_KINDS)}
+
+    def debug_advance(self, d, e, tau, nmax, literal=False):
+        d = np.ascontiguousarray(d, np.float32); e = np.ascontiguousarray(e, np.float32)
+        tau = np.ascontiguousarray(tau, np.float32); nmax = np.ascontiguousarray(nmax, np.int32)
+        out = np.empty_like(d); k = np.empty_like(nmax)
+        self._ck(self.lib.vt_debug_advance(self.h, _fp(d), _fp(e), _fp(tau), _ip(nmax), d.size, _fp(out), _ip(k), 1 if literal else 0))
+        return out, k
+
+    def set_empty_skip(self, mode):
+        self._ck(self.lib.vt_set_empty_skip(self.h, int(mode)))
 
     def set_wavefront_lanes(self, n):
         self._ck(self.lib.vt_set_wavefront_lanes(self.h, int(n)))

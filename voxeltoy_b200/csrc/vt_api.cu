@@ -27,6 +27,9 @@ struct vt_ctx {
     // volume
     int X = 0, Y = 0, Z = 0, BX = 0, BY = 0, BZ = 0;     // voxel and brick counts; the brick array is padded by one brick per side
     int PBX = 0, PBY = 0, PBZ = 0;                         // padded brick counts (strides)
+    // empty-space distance field over 8^3 cells (two buffers: the relaxation ping-pongs), see dda_skip
+    unsigned char* d_dist[2] = {nullptr, nullptr}; int CX = 0, CY = 0, CZ = 0; int dist_cur = 0; bool dist_valid = false;
+    int skip_mode = 1;                                     // 0 off, 1 auto (volumes with every side >= 64 voxels), 2 always
     int32_t* d_mat = nullptr;
     unsigned long long* d_bricks_alloc = nullptr;         // padded array
     unsigned long long* d_bricks = nullptr;               // brick (0,0,0): d_bricks_alloc + 1 + PBX + PBX*PBY
@@ -130,6 +133,7 @@ int vt_create(int device, vt_ctx** out)
     }
     c->stream = c->own_stream;
     if (const char* e = getenv("VT_WF_MAX_PATHS")) { const long long v = atoll(e); if (v > 0) c->wf_max_paths = (size_t)v; }   // tuning knob
+    if (const char* e = getenv("VT_EMPTY_SKIP")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->skip_mode = v; }
     if (const char* e = getenv("VT_WF_LANES")) { const int v = atoi(e); if (v >= 1 && v <= vt_ctx::kWfLanes) c->wf_lanes = v; }
     if (const char* e = getenv("VT_KERNEL_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->variant = v; }
     Shared sh;
@@ -160,7 +164,7 @@ void vt_destroy(vt_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_materials); cudaFree(c->d_emissive);
+    cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]); cudaFree(c->d_materials); cudaFree(c->d_emissive);
     cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum);
     cudaFree(c->d_guide_v); cudaFree(c->d_guide_u);
     for (int k = 0; k < vt_ctx::kWfLanes; ++k) {
@@ -202,14 +206,17 @@ static int alloc_volume(vt_ctx* c, int X, int Y, int Z)
 {
     VT_REQ(c, X > 0 && Y > 0 && Z > 0 && X <= 2048 && Y <= 2048 && Z <= 2048, "volume resolution must be in [1, 2048]^3");
     if (X != c->X || Y != c->Y || Z != c->Z || !c->d_mat) {
-        cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc);
-        c->d_mat = nullptr; c->d_bricks = nullptr; c->d_bricks_alloc = nullptr;
+        cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]);
+        c->d_mat = nullptr; c->d_bricks = nullptr; c->d_bricks_alloc = nullptr; c->d_dist[0] = c->d_dist[1] = nullptr; c->dist_valid = false;
         c->X = X; c->Y = Y; c->Z = Z;
         c->BX = (X + 3) / 4; c->BY = (Y + 3) / 4; c->BZ = (Z + 3) / 4;
         c->PBX = c->BX + 2; c->PBY = c->BY + 2; c->PBZ = c->BZ + 2;
         VT_CUDA(c, cudaMalloc(&c->d_mat, sizeof(int32_t) * (size_t)X * Y * Z));
         VT_CUDA(c, cudaMalloc(&c->d_bricks_alloc, sizeof(unsigned long long) * (size_t)c->PBX * c->PBY * c->PBZ));
         c->d_bricks = c->d_bricks_alloc + (1 + (size_t)c->PBX + (size_t)c->PBX * c->PBY);
+        c->CX = (X + 7) / 8; c->CY = (Y + 7) / 8; c->CZ = (Z + 7) / 8;
+        VT_CUDA(c, cudaMalloc(&c->d_dist[0], (size_t)c->CX * c->CY * c->CZ));
+        VT_CUDA(c, cudaMalloc(&c->d_dist[1], (size_t)c->CX * c->CY * c->CZ));
     }
     volume_bounds(c);
     return VT_OK;
@@ -226,6 +233,23 @@ static int clear_occupancy(vt_ctx* c)
     return VT_OK;
 }
 
+// (re)builds the empty-space distance field from the bricks. Cheap (the cell grid is 1/512 of the voxels): run after every
+// change that can make an empty cell solid (upload, voxelize, add voxel). Removing voxels leaves it valid (lower bounds).
+static constexpr int kDistCap = 16;
+static int rebuild_dist(vt_ctx* c)
+{
+    const size_t nc = (size_t)c->CX * c->CY * c->CZ;
+    vt_dist_init_kernel<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_dist[0], c->X, c->Y, c->Z, c->PBX, c->PBX * c->PBY,
+                                                                 c->CX, c->CY, c->CZ, kDistCap);
+    int cur = 0;
+    for (int it = 0; it < kDistCap - 1; ++it, cur ^= 1)
+        vt_dist_relax_kernel<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->d_dist[cur], c->d_dist[cur ^ 1], c->CX, c->CY, c->CZ);
+    c->dist_cur = cur; c->dist_valid = true;
+    c->launches += kDistCap;
+    VT_CUDA(c, cudaGetLastError());
+    return VT_OK;
+}
+
 static int rebuild_occupancy(vt_ctx* c)
 {
     int rc = clear_occupancy(c);
@@ -233,6 +257,8 @@ static int rebuild_occupancy(vt_ctx* c)
     const size_t rows = (size_t)c->BX * c->Y * c->Z;
     vt_build_bricks_kernel<<<grid_for(rows, 256), 256, 0, c->stream>>>(c->d_mat, c->d_bricks, c->X, c->Y, c->Z, c->BX, c->PBX, c->PBX * c->PBY);
     c->launches += 1;
+    rc = rebuild_dist(c);
+    if (rc != VT_OK) return rc;
     VT_CUDA(c, cudaGetLastError());
     return VT_OK;
 }
@@ -457,6 +483,8 @@ static Volume make_volume(const vt_ctx* c)
     V.mat = c->d_mat; V.bricks = c->d_bricks;
     V.X = c->X; V.Y = c->Y; V.Z = c->Z;
     V.BX = c->PBX; V.BXY = c->PBX * c->PBY;               // strides of the padded brick array
+    const bool skip = c->dist_valid && (c->skip_mode == 2 || (c->skip_mode == 1 && std::min(c->X, std::min(c->Y, c->Z)) >= 64));
+    V.dist = skip ? c->d_dist[c->dist_cur] : nullptr; V.CX = c->CX; V.CXY = c->CX * c->CY;
     V.bmin.x = c->bmin[0]; V.bmin.y = c->bmin[1]; V.bmin.z = c->bmin[2];
     V.bmax.x = c->bmax[0]; V.bmax.y = c->bmax[1]; V.bmax.z = c->bmax[2];
     V.vsize.x = c->vsize[0]; V.vsize.y = c->vsize[1]; V.vsize.z = c->vsize[2];
@@ -549,6 +577,13 @@ int vt_get_kernel_times(vt_ctx* c, vt_kernel_times* out)
     c->timed.clear();
     return VT_OK;
 }
+int vt_set_empty_skip(vt_ctx* c, int mode)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, mode >= 0 && mode <= 2, "empty-skip mode must be 0 (off), 1 (auto) or 2 (on)");
+    c->skip_mode = mode;
+    return VT_OK;
+}
 int vt_set_wavefront_lanes(vt_ctx* c, int lanes)
 {
     if (!c) return VT_ERR_INVALID;
@@ -614,7 +649,7 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
     if (c->wf_shade_blocks[ci] == 0) {
         int per_sm_s = 0, per_sm_t = 0, sms = 0;
         VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, wf_shade_kernel<COUNT>, 128, 0));
-        VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, wf_trace_kernel<COUNT>, 256, 0));
+        VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, wf_trace_kernel<COUNT, true>, 256, 0));
         VT_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
         c->wf_shade_blocks[ci] = std::max(1, per_sm_s) * std::max(1, sms);
         c->wf_trace_blocks[ci] = std::max(1, per_sm_t) * std::max(1, sms);
@@ -650,7 +685,8 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
             // it == 0: primary rays; it >= 1: the shadow + bounce rays emitted by wf_shade(it)
             // generation `it` lives in buf[it & 1]; wf_shade compacts its survivors into buf[(it + 1) & 1]
             const WfBuf& cur = S.buf[it & 1]; const WfBuf& nxt = S.buf[(it + 1) & 1];
-            { WfTimer t(c, VT_K_TRACE, st); wf_trace_kernel<COUNT><<<c->wf_trace_blocks[ci], 256, 0, st>>>(V, S, cur, cn + it, c->d_counters); }
+            { WfTimer t(c, VT_K_TRACE, st); if (V.dist != nullptr && !COUNT) wf_trace_kernel<COUNT, true><<<c->wf_trace_blocks[ci], 256, 0, st>>>(V, S, cur, cn + it, c->d_counters);
+              else wf_trace_kernel<COUNT, false><<<c->wf_trace_blocks[ci], 256, 0, st>>>(V, S, cur, cn + it, c->d_counters); }
             { WfTimer t(c, VT_K_CLASSIFY, st); wf_classify_kernel<<<classify_blocks, 256, 0, st>>>(V, F, L, S, cur, pass0, cn + it, cn + it + 1, it == 0 ? prim : nullptr); }
             { WfTimer t(c, VT_K_SHADE, st); wf_shade_kernel<COUNT><<<c->wf_shade_blocks[ci], 128, 0, st>>>(V, F, S, cur, nxt, cn + it + 1, c->d_counters); }
             c->launches += 3;
@@ -795,6 +831,8 @@ int vt_voxelize(vt_ctx* c, const float* xyz, size_t n_verts, const uint32_t* ind
     }
     vt_fill_offsets_kernel<<<grid_for((size_t)c->BX * Y * Z, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_mat, X, Y, Z, c->BX, c->PBX, c->PBX * c->PBY, fill);
     c->launches += 1;
+    rc = rebuild_dist(c);
+    if (rc != VT_OK) return rc;
     VT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     VT_CUDA(c, cudaGetLastError());
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -856,6 +894,8 @@ int vt_add_voxel(vt_ctx* c, float mx, float my)
     vt_add_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), make_frame(c), mx, my, c->d_shared, c->d_mat, c->d_bricks, c->d_result);
     c->launches += 1;
     VT_CUDA(c, cudaGetLastError());
+    rc = rebuild_dist(c);                                   // an empty cell may have become solid
+    if (rc != VT_OK) return rc;
     return VT_OK;
 }
 int vt_remove_voxel(vt_ctx* c)
@@ -865,6 +905,28 @@ int vt_remove_voxel(vt_ctx* c)
     vt_remove_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), c->d_shared, c->d_mat, c->d_bricks, c->d_result);
     c->launches += 1;
     VT_CUDA(c, cudaGetLastError());
+    return VT_OK;
+}
+
+int vt_debug_advance(vt_ctx* c, const float* d, const float* e, const float* tau, const int32_t* nmax, size_t n, float* d_out, int32_t* k_out, int literal)
+{
+    if (!c || !d || !e || !tau || !nmax || !d_out || !k_out) return VT_ERR_INVALID;
+    if (n == 0) return VT_OK;
+    VT_BIND(c);
+    float *dd = nullptr, *de = nullptr, *dt = nullptr, *dout = nullptr; int *dn = nullptr, *dk = nullptr;
+    VT_CUDA(c, cudaMalloc(&dd, n * 4)); VT_CUDA(c, cudaMalloc(&de, n * 4)); VT_CUDA(c, cudaMalloc(&dt, n * 4));
+    VT_CUDA(c, cudaMalloc(&dout, n * 4)); VT_CUDA(c, cudaMalloc(&dn, n * 4)); VT_CUDA(c, cudaMalloc(&dk, n * 4));
+    VT_CUDA(c, cudaMemcpyAsync(dd, d, n * 4, cudaMemcpyHostToDevice, c->stream));
+    VT_CUDA(c, cudaMemcpyAsync(de, e, n * 4, cudaMemcpyHostToDevice, c->stream));
+    VT_CUDA(c, cudaMemcpyAsync(dt, tau, n * 4, cudaMemcpyHostToDevice, c->stream));
+    VT_CUDA(c, cudaMemcpyAsync(dn, nmax, n * 4, cudaMemcpyHostToDevice, c->stream));
+    vt_advance_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(dd, de, dt, dn, n, dout, dk, literal);
+    c->launches += 1;
+    VT_CUDA(c, cudaGetLastError());
+    VT_CUDA(c, cudaMemcpyAsync(d_out, dout, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaMemcpyAsync(k_out, dk, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dd); cudaFree(de); cudaFree(dt); cudaFree(dout); cudaFree(dn); cudaFree(dk);
     return VT_OK;
 }
 

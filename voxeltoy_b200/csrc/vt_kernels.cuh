@@ -212,6 +212,43 @@ __global__ void vt_sentinel_kernel(unsigned long long* __restrict__ padded, int 
     }
 }
 
+// ---- empty-space distance field (Volume::dist, dda_skip) ----------------------------------------------------------
+// pass 0: one thread per 8^3 cell: 0 if any in-volume voxel of its 2x2x2 bricks is set, else `cap`
+__global__ void vt_dist_init_kernel(const unsigned long long* __restrict__ bricks, unsigned char* __restrict__ dist,
+                                    int X, int Y, int Z, int PBX, int BXY, int CX, int CY, int CZ, int cap)
+{
+    const int n = CX * CY * CZ;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int cx = i % CX, r = i / CX, cy = r % CY, cz = r / CY;
+        bool solid = false;
+        for (int b = 0; b < 8 && !solid; ++b) {
+            const int bx = 2 * cx + (b & 1), by = 2 * cy + ((b >> 1) & 1), bz = 2 * cz + (b >> 2);
+            if (bx * 4 >= X || by * 4 >= Y || bz * 4 >= Z) continue;
+            unsigned long long w = __ldg(bricks + ((long long)bx + (long long)by * PBX + (long long)bz * BXY));
+            if (w == 0ull) continue;
+            if (bx * 4 + 3 < X && by * 4 + 3 < Y && bz * 4 + 3 < Z) { solid = true; break; }
+            for (int k = 0; k < 64; ++k)                              // brick straddles the boundary: ignore the sentinel bits
+                if (((w >> k) & 1ull) && bx * 4 + (k & 3) < X && by * 4 + ((k >> 2) & 3) < Y && bz * 4 + (k >> 4) < Z) { solid = true; break; }
+        }
+        dist[i] = solid ? 0 : (unsigned char)cap;
+    }
+}
+// one relaxation of the Chebyshev distance transform: d(c) = min(d(c), 1 + min over the 26 neighbours)
+__global__ void vt_dist_relax_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int CX, int CY, int CZ)
+{
+    const int n = CX * CY * CZ;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int cx = i % CX, r = i / CX, cy = r % CY, cz = r / CY;
+        int d = in[i];
+        for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+            const int x = cx + dx, y = cy + dy, z = cz + dz;
+            if ((unsigned)x >= (unsigned)CX || (unsigned)y >= (unsigned)CY || (unsigned)z >= (unsigned)CZ) continue;
+            d = min(d, (int)in[x + y * CX + z * CX * CY] + 1);
+        }
+        out[i] = (unsigned char)d;
+    }
+}
+
 // material-offset grid from occupancy: voxel = bit ? fill : -1. One thread per x-run of 4 voxels.
 __global__ void vt_fill_offsets_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
                                        int X, int Y, int Z, int BX, int PBX, int BXY, int fill)
@@ -340,6 +377,18 @@ __global__ void vt_assign_materials_kernel(int* __restrict__ mat, int X, int Y, 
         if (rule == 1) id = ((x >> 5) ^ (y >> 5) ^ (z >> 5)) % n_table;
         mat[i] = __ldg(table + id);
     }
+}
+
+// test hook: advance_until on explicit operands, next to the literal loop it replaces
+__global__ void vt_advance_kernel(const float* __restrict__ d, const float* __restrict__ e, const float* __restrict__ tau,
+                                  const int* __restrict__ nmax, size_t n, float* __restrict__ d_out, int* __restrict__ k_out, int literal)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = d[i]; int k = 0;
+    if (literal) { while (x <= tau[i] && k < nmax[i]) { x = x + e[i]; ++k; } }
+    else k = advance_until(x, e[i], tau[i], nmax[i]);
+    d_out[i] = x; k_out[i] = k;
 }
 
 // test hook: the DDA alone

@@ -41,7 +41,8 @@ constexpr int kWfQueues = 5;          // 0 = finish, 1..3 = material type 0..2, 
 #endif
 constexpr int kWfLiveMin = VT_WF_LIVE_MIN;        // refill the warp when fewer lanes than this hold a ray
 constexpr int kWfStepChunk = 4;       // DDA iterations between two refill checks
-constexpr int kWfGrab = 128;          // rays a warp reserves per atomic on the hand-out counter
+constexpr int kWfGrab = 128;
+constexpr int kWfSkipMinLanes = 12;   // lanes that must want an empty-space skip before the warp pays for one          // rays a warp reserves per atomic on the hand-out counter
 
 enum { WF_RAY_SHADOW = 0, WF_RAY_BOUNCE = 1, WF_RAY_PRIMARY = 2 };
 enum { WF_HIT_VOXEL = 1, WF_HIT_GROUND = 2, WF_HIT_PRIMARY = 16 };    // hit.w flags (+ nanmask << 8)
@@ -266,7 +267,7 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
 // wf_trace: the loop of dda.h:38-57 for every ray record of the queue. Persistent warps; a warp reserves kWfGrab
 // rays per atomic and its lanes refill from that range whenever fewer than kWfLiveMin of them hold a ray.
 // ---------------------------------------------------------------------------------------------------------
-template <bool COUNT>
+template <bool COUNT, bool SKIP>
 __global__ void __launch_bounds__(256)
 wf_trace_kernel(const Volume V, const WfState S, const WfBuf out, WfCounts* __restrict__ cnt, Counters* __restrict__ counters)
 {
@@ -276,6 +277,9 @@ wf_trace_kernel(const Volume V, const WfState S, const WfBuf out, WfCounts* __re
     const unsigned int n_rays = (unsigned int)(cnt->tq_rq >> 32);
     Tally<COUNT> tl; tl.clear();
 
+#ifdef VT_SKIP_STATS
+    unsigned long long dbg_calls = 0, dbg_ok = 0, dbg_steps = 0;
+#endif
     bool have = false, exhausted = false;
     unsigned int range_next = 0, range_end = 0;     // warp-uniform
     unsigned int pid = 0;                           // slot of the ray's path in `out`
@@ -321,6 +325,23 @@ wf_trace_kernel(const Volume V, const WfState S, const WfBuf out, WfCounts* __re
         for (int k = 0; k < kWfStepChunk; ++k)
             if (have && status == DDA_RUNNING) status = dda_step<COUNT>(V, s, tl);
         if (++chunks > chunk_guard && status == DDA_RUNNING) status = DDA_NOHIT;
+        if (SKIP && !COUNT) {                     // counting builds step every voxel so that S stays the algorithmic count
+            // the cheap part (one byte per lane) runs converged; the skip itself only when enough lanes want it, so that its
+            // divergent set-up is not paid for one or two lanes while the rest of the warp idles
+            const bool running = have && status == DDA_RUNNING;
+            const int radius = running ? dda_skip_radius(V, s) : 0;
+            const unsigned m_run = __ballot_sync(full, running), m_want = __ballot_sync(full, radius >= 2);
+            if (m_want != 0u && (__popc(m_want) >= kWfSkipMinLanes || 2 * __popc(m_want) >= __popc(m_run))) {
+                if (radius >= 2) {
+                    const int skipped = dda_skip(V, s, radius);
+#ifdef VT_SKIP_STATS
+                    dbg_calls += 1; dbg_ok += skipped > 0; dbg_steps += skipped;
+#else
+                    (void)skipped;
+#endif
+                }
+            }
+        }
         // ---- retire finished rays --------------------------------------------------------------------------
         if (have && status != DDA_RUNNING) {
             if (type == WF_RAY_SHADOW) out.vis[pid] = wf_light_visible(V, aux, status, s);
@@ -328,6 +349,9 @@ wf_trace_kernel(const Volume V, const WfState S, const WfBuf out, WfCounts* __re
             have = false;
         }
     }
+#ifdef VT_SKIP_STATS
+    if (SKIP) { atomicAdd(&counters->E, dbg_calls); atomicAdd(&counters->Q, dbg_ok); atomicAdd(&counters->H, dbg_steps); }
+#endif
     wf_flush_tally<COUNT>(tl, counters);
 }
 
