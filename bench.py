@@ -271,6 +271,12 @@ def main():
     achieved = trace_bytes_per_launch / (trace_ms_per_launch * 1e-3) / 1e9
     step_achieved = bps * npx * PASSES / (ms_kernel * 1e-3) / 1e9     # every kernel of the step, all algorithmic bytes
     kernel_ms_total = sum(v[0] for v in ktimes.values())
+    # L2 read bandwidth of this GPU, measured now (the north star's roofline for this path is L2, not HBM: the grid, the noise
+    # table and the CDFs are L2-resident). 48 MiB buffer, 16-byte ld.global.cg, all SMs.
+    try:
+        l2_gbs = max(ctx.measure_l2_bandwidth(48 << 20, 20) for _ in range(3))
+    except Exception:
+        l2_gbs = None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -302,6 +308,8 @@ def main():
                          "per_sample": {"S": cnt["dda_steps"] / n_samp, "R": cnt["rand_calls"] / n_samp,
                                         "H": cnt["material_evals"] / n_samp, "E": cnt["cdf_loads"] / n_samp,
                                         "Q": cnt["env_lookups"] / n_samp},
+                         "l2": {"peak": l2_gbs, "unit": "GB/s", "how": "measured live: 48 MiB buffer, ld.global.cg 16 B, 148x8 CTAs, best of 3",
+                                "trace_frac": (achieved / l2_gbs) if l2_gbs else None, "step_frac": (step_achieved / l2_gbs) if l2_gbs else None},
                          "note": "issue-bound, not bandwidth-bound: see profiles/ (issue slots busy, lanes per instruction)"},
         }
         # second half of BASELINE's metric: voxelize ms @512^3 (bunny.obj through the host MeshLoader + GPUVoxelizer path;

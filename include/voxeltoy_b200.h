@@ -184,6 +184,9 @@ const char* vt_version(void);
 /* test hook: trace n rays (origin xyz, dir xyz interleaved, 6 floats each) through the current volume with
  * the DDA of dda.h:63-100; out_hit[4n] = (x,y,z, code) with code 1 voxel hit, 2 ground, 0 miss. */
 int vt_debug_trace_rays(vt_ctx* ctx, const float* rays, size_t n, float* out_hit);
+/* measurement hook: L2 read bandwidth in GB/s (16-byte ld.global.cg over a `bytes`-sized buffer that fits in L2, `reps`
+ * sweeps, all SMs) -- the denominator for the L2 roofline the north star asks for; MEASURED_PEAKS.json only has HBM. */
+int vt_measure_l2_bandwidth(vt_ctx* ctx, size_t bytes, int reps, float* gb_per_s);
 /* test hook: for each i, d[i] <- fl(d[i] + e[i]) while d[i] <= tau[i], at most nmax[i] times; k_out = additions done.
  * literal = 1 runs the plain loop, 0 the closed form used by the empty-space skip (advance_until). Operands must be > 0. */
 int vt_debug_advance(vt_ctx* ctx, const float* d, const float* e, const float* tau, const int32_t* nmax, size_t n,

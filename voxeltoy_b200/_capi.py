@@ -73,6 +73,7 @@ SIGNATURES = {
     "vt_set_wavefront_max_paths": (C.c_int, [P, C.c_size_t]),
     "vt_set_wavefront_lanes": (C.c_int, [P, C.c_int]),
     "vt_set_empty_skip": (C.c_int, [P, C.c_int]),
+    "vt_measure_l2_bandwidth": (C.c_int, [P, C.c_size_t, C.c_int, f32p]),
     "vt_debug_advance": (C.c_int, [P, f32p, f32p, f32p, i32p, C.c_size_t, f32p, i32p, C.c_int]),
     "vt_counters_enable": (C.c_int, [P, C.c_int]),
     "vt_get_counters": (C.c_int, [P, C.POINTER(VtCounters)]),
@@ -305,6 +306,11 @@ class Context:
         out = np.empty_like(d); k = np.empty_like(nmax)
         self._ck(self.lib.vt_debug_advance(self.h, _fp(d), _fp(e), _fp(tau), _ip(nmax), d.size, _fp(out), _ip(k), 1 if literal else 0))
         return out, k
+
+    def measure_l2_bandwidth(self, nbytes=48 << 20, reps=20):
+        g = C.c_float()
+        self._ck(self.lib.vt_measure_l2_bandwidth(self.h, int(nbytes), int(reps), C.cast(C.byref(g), f32p)))
+        return float(g.value)
 
     def set_empty_skip(self, mode):
         self._ck(self.lib.vt_set_empty_skip(self.h, int(mode)))

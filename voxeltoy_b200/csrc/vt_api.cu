@@ -242,10 +242,10 @@ static int rebuild_dist(vt_ctx* c)
     vt_dist_init_kernel<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_dist[0], c->X, c->Y, c->Z, c->PBX, c->PBX * c->PBY,
                                                                  c->CX, c->CY, c->CZ, kDistCap);
     int cur = 0;
-    for (int it = 0; it < kDistCap - 1; ++it, cur ^= 1)
-        vt_dist_relax_kernel<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->d_dist[cur], c->d_dist[cur ^ 1], c->CX, c->CY, c->CZ);
+    for (int axis = 0; axis < 3; ++axis, cur ^= 1)
+        vt_dist_pass_kernel<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->d_dist[cur], c->d_dist[cur ^ 1], c->CX, c->CY, c->CZ, axis, kDistCap);
     c->dist_cur = cur; c->dist_valid = true;
-    c->launches += kDistCap;
+    c->launches += 4;
     VT_CUDA(c, cudaGetLastError());
     return VT_OK;
 }
@@ -905,6 +905,29 @@ int vt_remove_voxel(vt_ctx* c)
     vt_remove_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), c->d_shared, c->d_mat, c->d_bricks, c->d_result);
     c->launches += 1;
     VT_CUDA(c, cudaGetLastError());
+    return VT_OK;
+}
+
+int vt_measure_l2_bandwidth(vt_ctx* c, size_t bytes, int reps, float* gbs)
+{
+    if (!c || !gbs || bytes < 4096 || reps < 1) return VT_ERR_INVALID;
+    VT_BIND(c);
+    uint4* buf = nullptr; unsigned int* sink = nullptr;
+    VT_CUDA(c, cudaMalloc(&buf, bytes)); VT_CUDA(c, cudaMalloc(&sink, 4));
+    VT_CUDA(c, cudaMemsetAsync(buf, 1, bytes, c->stream));
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const size_t n_vec = bytes / 16;
+    vt_l2_read_kernel<<<sms * 8, 256, 0, c->stream>>>(buf, n_vec, 2, sink);          // warm: pull the buffer into L2
+    VT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    vt_l2_read_kernel<<<sms * 8, 256, 0, c->stream>>>(buf, n_vec, reps, sink);
+    VT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    c->launches += 2;
+    VT_CUDA(c, cudaGetLastError());
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    VT_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *gbs = (float)((double)n_vec * 16.0 * reps / (ms * 1e-3) / 1e9);
+    cudaFree(buf); cudaFree(sink);
     return VT_OK;
 }
 

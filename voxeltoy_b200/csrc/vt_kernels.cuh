@@ -233,17 +233,21 @@ __global__ void vt_dist_init_kernel(const unsigned long long* __restrict__ brick
         dist[i] = solid ? 0 : (unsigned char)cap;
     }
 }
-// one relaxation of the Chebyshev distance transform: d(c) = min(d(c), 1 + min over the 26 neighbours)
-__global__ void vt_dist_relax_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int CX, int CY, int CZ)
+// Chebyshev distance transform, separable: d(c) = min over (jx, jy, jz) of max(|jx|, |jy|, |jz|) with solid(c + j)
+//   = min_jz max(|jz|, min_jy max(|jy|, min_jx max(|jx|, [0 if solid(c + j) else cap]))) -- one 1-D pass per axis.
+// axis: 0 x, 1 y, 2 z; values are capped at `cap`; cells outside the grid impose nothing.
+__global__ void vt_dist_pass_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int CX, int CY, int CZ, int axis, int cap)
 {
     const int n = CX * CY * CZ;
+    const int stride = (axis == 0) ? 1 : (axis == 1 ? CX : CX * CY);
+    const int len = (axis == 0) ? CX : (axis == 1 ? CY : CZ);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int cx = i % CX, r = i / CX, cy = r % CY, cz = r / CY;
+        const int p = (axis == 0) ? cx : (axis == 1 ? cy : cz);
         int d = in[i];
-        for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
-            const int x = cx + dx, y = cy + dy, z = cz + dz;
-            if ((unsigned)x >= (unsigned)CX || (unsigned)y >= (unsigned)CY || (unsigned)z >= (unsigned)CZ) continue;
-            d = min(d, (int)in[x + y * CX + z * CX * CY] + 1);
+        for (int j = 1; j < cap && j < d; ++j) {
+            if (p - j >= 0) d = min(d, max(j, (int)in[i - j * stride]));
+            if (p + j < len) d = min(d, max(j, (int)in[i + j * stride]));
         }
         out[i] = (unsigned char)d;
     }
@@ -377,6 +381,23 @@ __global__ void vt_assign_materials_kernel(int* __restrict__ mat, int X, int Y, 
         if (rule == 1) id = ((x >> 5) ^ (y >> 5) ^ (z >> 5)) % n_table;
         mat[i] = __ldg(table + id);
     }
+}
+
+// measurement hook: L2 read bandwidth (the north star quotes the path tracer against the L2 roofline, and the driver's
+// MEASURED_PEAKS.json only has HBM). Every thread streams 16-byte loads (ld.global.cg: cached in L2, not L1) over a buffer
+// that fits in L2, `reps` times.
+__global__ void __launch_bounds__(256)
+vt_l2_read_kernel(const uint4* __restrict__ buf, size_t n_vec, int reps, unsigned int* __restrict__ sink)
+{
+    unsigned int acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < reps; ++r)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+            uint4 v;
+            asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(buf + i));
+            acc ^= v.x ^ v.y ^ v.z ^ v.w;
+        }
+    if (acc == 0x12345678u) *sink = acc;
 }
 
 // test hook: advance_until on explicit operands, next to the literal loop it replaces
