@@ -40,7 +40,10 @@ constexpr int kWfQueues = 5;          // 0 = finish, 1..3 = material type 0..2, 
 #define VT_WF_SHADE_MIN_BLOCKS 8
 #endif
 constexpr int kWfLiveMin = VT_WF_LIVE_MIN;        // refill the warp when fewer lanes than this hold a ray
-constexpr int kWfStepChunk = 4;       // DDA iterations between two refill checks
+#ifndef VT_WF_STEP_CHUNK
+#define VT_WF_STEP_CHUNK 8
+#endif
+constexpr int kWfStepChunk = VT_WF_STEP_CHUNK;   // 3..16 measured: flat above 6 (refill checks amortised), 8 kept       // DDA iterations between two refill checks
 constexpr int kWfGrab = 128;
 constexpr int kWfSkipMinLanes = 12;   // lanes that must want an empty-space skip before the warp pays for one          // rays a warp reserves per atomic on the hand-out counter
 
