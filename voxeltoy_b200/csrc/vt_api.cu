@@ -33,6 +33,8 @@ struct vt_ctx {
     int32_t* d_mat = nullptr;
     unsigned long long* d_bricks_alloc = nullptr;         // padded array
     unsigned long long* d_bricks = nullptr;               // brick (0,0,0): d_bricks_alloc + 1 + PBX + PBX*PBY
+    unsigned long long* d_bricks_empty = nullptr;         // template of the empty grid (sentinel shell only): clearing is one D2D copy
+    cudaStream_t aux_stream = nullptr; cudaEvent_t aux_fork = nullptr, aux_join = nullptr;   // side stream of vt_voxelize
     float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0}, vsize[3] = {0, 0, 0};
     // scene arrays
     float* d_materials = nullptr; size_t n_materials = 0;
@@ -164,7 +166,7 @@ void vt_destroy(vt_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]); cudaFree(c->d_materials); cudaFree(c->d_emissive);
+    cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_bricks_empty); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]); cudaFree(c->d_materials); cudaFree(c->d_emissive);
     cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum);
     cudaFree(c->d_guide_v); cudaFree(c->d_guide_u);
     for (int k = 0; k < vt_ctx::kWfLanes; ++k) {
@@ -179,6 +181,9 @@ void vt_destroy(vt_ctx* c)
     cudaFree(c->d_primary); cudaFree(c->d_work); cudaFree(c->d_shared); cudaFree(c->d_result); cudaFree(c->d_counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->aux_fork) cudaEventDestroy(c->aux_fork);
+    if (c->aux_join) cudaEventDestroy(c->aux_join);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -206,14 +211,22 @@ static int alloc_volume(vt_ctx* c, int X, int Y, int Z)
 {
     VT_REQ(c, X > 0 && Y > 0 && Z > 0 && X <= 2048 && Y <= 2048 && Z <= 2048, "volume resolution must be in [1, 2048]^3");
     if (X != c->X || Y != c->Y || Z != c->Z || !c->d_mat) {
-        cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]);
-        c->d_mat = nullptr; c->d_bricks = nullptr; c->d_bricks_alloc = nullptr; c->d_dist[0] = c->d_dist[1] = nullptr; c->dist_valid = false;
+        cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_bricks_empty); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]);
+        c->d_mat = nullptr; c->d_bricks = nullptr; c->d_bricks_alloc = nullptr; c->d_bricks_empty = nullptr; c->d_dist[0] = c->d_dist[1] = nullptr; c->dist_valid = false;
         c->X = X; c->Y = Y; c->Z = Z;
         c->BX = (X + 3) / 4; c->BY = (Y + 3) / 4; c->BZ = (Z + 3) / 4;
         c->PBX = c->BX + 2; c->PBY = c->BY + 2; c->PBZ = c->BZ + 2;
         VT_CUDA(c, cudaMalloc(&c->d_mat, sizeof(int32_t) * (size_t)X * Y * Z));
         VT_CUDA(c, cudaMalloc(&c->d_bricks_alloc, sizeof(unsigned long long) * (size_t)c->PBX * c->PBY * c->PBZ));
         c->d_bricks = c->d_bricks_alloc + (1 + (size_t)c->PBX + (size_t)c->PBX * c->PBY);
+        {   // the empty template: zero inside the volume, the sentinel shell set (see dda_step); built once per resolution
+            const size_t npb = (size_t)c->PBX * c->PBY * c->PBZ;
+            VT_CUDA(c, cudaMalloc(&c->d_bricks_empty, npb * 8));
+            VT_CUDA(c, cudaMemsetAsync(c->d_bricks_empty, 0, npb * 8, c->stream));
+            vt_sentinel_kernel<<<grid_for(npb, 256), 256, 0, c->stream>>>(c->d_bricks_empty, X, Y, Z, c->PBX, c->PBY, c->PBZ);
+            c->launches += 1;
+            VT_CUDA(c, cudaGetLastError());
+        }
         c->CX = (X + 7) / 8; c->CY = (Y + 7) / 8; c->CZ = (Z + 7) / 8;
         VT_CUDA(c, cudaMalloc(&c->d_dist[0], (size_t)c->CX * c->CY * c->CZ));
         VT_CUDA(c, cudaMalloc(&c->d_dist[1], (size_t)c->CX * c->CY * c->CZ));
@@ -227,9 +240,7 @@ static int alloc_volume(vt_ctx* c, int X, int Y, int Z)
 static int clear_occupancy(vt_ctx* c)
 {
     const size_t npb = (size_t)c->PBX * c->PBY * c->PBZ;
-    VT_CUDA(c, cudaMemsetAsync(c->d_bricks_alloc, 0, npb * 8, c->stream));
-    vt_sentinel_kernel<<<grid_for(npb, 256), 256, 0, c->stream>>>(c->d_bricks_alloc, c->X, c->Y, c->Z, c->PBX, c->PBY, c->PBZ);
-    c->launches += 1;
+    VT_CUDA(c, cudaMemcpyAsync(c->d_bricks_alloc, c->d_bricks_empty, npb * 8, cudaMemcpyDeviceToDevice, c->stream));
     return VT_OK;
 }
 
@@ -821,7 +832,18 @@ int vt_voxelize(vt_ctx* c, const float* xyz, size_t n_verts, const uint32_t* ind
     VT_CUDA(c, cudaMemcpyAsync(d_M, M, 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     const int n_tris = (int)(n_indices / 3);
     // timed region: clear + scatter + derive (kernel time incl. grid clear, excl. OBJ parse and H2D)
+    if (!c->aux_stream) {
+        VT_CUDA(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        VT_CUDA(c, cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
+        VT_CUDA(c, cudaEventCreateWithFlags(&c->aux_join, cudaEventDisableTiming));
+    }
     VT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    // the R32I grid is cleared to -1 by the copy engine path (HBM-write bound) on a side stream while the triangles are
+    // scattered into the bit grid (latency bound); the solid voxels' offsets are patched in afterwards
+    VT_CUDA(c, cudaEventRecord(c->aux_fork, c->stream));
+    VT_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->aux_fork, 0));
+    VT_CUDA(c, cudaMemsetAsync(c->d_mat, 0xff, sizeof(int32_t) * (size_t)X * Y * Z, c->aux_stream));
+    VT_CUDA(c, cudaEventRecord(c->aux_join, c->aux_stream));
     rc = clear_occupancy(c);
     if (rc != VT_OK) return rc;
     if (n_tris > 0) {
@@ -829,7 +851,8 @@ int vt_voxelize(vt_ctx* c, const float* xyz, size_t n_verts, const uint32_t* ind
         vt_voxelize_kernel<<<ctas, 128, 0, c->stream>>>(d_xyz, d_idx, n_tris, d_M, X, Y, Z, c->PBX, c->PBX * c->PBY, c->d_bricks);
         c->launches += 1;
     }
-    vt_fill_offsets_kernel<<<grid_for((size_t)c->BX * Y * Z, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_mat, X, Y, Z, c->BX, c->PBX, c->PBX * c->PBY, fill);
+    VT_CUDA(c, cudaStreamWaitEvent(c->stream, c->aux_join, 0));
+    vt_fill_solid_kernel<<<grid_for((size_t)c->BX * c->BY * c->BZ, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_mat, X, Y, Z, c->BX, c->BY, c->BZ, c->PBX, c->PBX * c->PBY, fill);
     c->launches += 1;
     rc = rebuild_dist(c);
     if (rc != VT_OK) return rc;

@@ -276,6 +276,25 @@ __global__ void vt_fill_offsets_kernel(const unsigned long long* __restrict__ br
     }
 }
 
+// sparse variant used by vt_voxelize: the grid was cleared to -1 by a memset; one thread per brick patches `fill` into the
+// voxels whose bit is set (in-volume bits only: boundary bricks also carry sentinel bits)
+__global__ void vt_fill_solid_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
+                                     int X, int Y, int Z, int BX, int BY, int BZ, int PBX, int BXY, int fill)
+{
+    const size_t n = (size_t)BX * BY * BZ;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int bx = (int)(i % BX); const size_t r = i / BX;
+        const int by = (int)(r % BY), bz = (int)(r / BY);
+        unsigned long long w = __ldg(bricks + ((long long)bx + (long long)by * PBX + (long long)bz * BXY));
+        while (w != 0ull) {
+            const int k = __ffsll((long long)w) - 1;
+            w &= w - 1ull;
+            const int x = bx * 4 + (k & 3), y = by * 4 + ((k >> 2) & 3), z = bz * 4 + (k >> 4);
+            if (x < X && y < Y && z < Z) mat[(size_t)x + (size_t)y * X + (size_t)z * X * Y] = fill;
+        }
+    }
+}
+
 // ---- voxelizer --------------------------------------------------------------------------------
 // voxelize.vs:20-28 + voxelize.gs:55-251 (THIN). One warp per triangle; lanes stride over the (x,y)
 // columns of the swizzled bounding box, each column resolves its short z-range. The set of voxels
