@@ -320,7 +320,9 @@ def main():
             for _ in range(5):
                 r2.loadMesh(os.path.join(ROOT, "tests", "golden", "bunny.obj.gz"), 512)
                 ms.append(r2.context().last_voxelize_ms())
-            vbytes = 512 ** 3 / 8 * 2 + 512 ** 3 * 4          # clear + read of the bit grid, write of the int32 offset grid
+            # bit grid: template copy (read + write), scatter, read by the sparse offset patch and by the distance-field pass;
+            # the int32 entries of EMPTY voxels are cleared lazily, on read-back (the reference never clears them: SURVEY U5)
+            vbytes = 512 ** 3 / 8 * 4
             line["voxelize"] = {"metric": "voxelize ms @512^3", "value": min(ms), "unit": "ms", "mesh": "bunny.obj (4968 triangles)",
                                 "runs_ms": ms, "algorithmic_bytes": vbytes, "achieved_gbs": vbytes / (min(ms) * 1e-3) / 1e9,
                                 "frac_of_hbm_peak": vbytes / (min(ms) * 1e-3) / 1e9 / peak}

@@ -28,13 +28,16 @@ struct vt_ctx {
     int X = 0, Y = 0, Z = 0, BX = 0, BY = 0, BZ = 0;     // voxel and brick counts; the brick array is padded by one brick per side
     int PBX = 0, PBY = 0, PBZ = 0;                         // padded brick counts (strides)
     // empty-space distance field over 8^3 cells (two buffers: the relaxation ping-pongs), see dda_skip
-    unsigned char* d_dist[2] = {nullptr, nullptr}; int CX = 0, CY = 0, CZ = 0; int dist_cur = 0; bool dist_valid = false;
+    unsigned char* d_dist[2] = {nullptr, nullptr}; int CX = 0, CY = 0, CZ = 0; int dist_cur = 0; bool dist_valid = false;   // dist_valid false: rebuilt before the next render that uses it
     int skip_mode = 1;                                     // 0 off, 1 auto (volumes with every side >= 64 voxels), 2 always
     int32_t* d_mat = nullptr;
+    // vt_voxelize writes the offsets of the solid voxels only (as the reference's imageStore scatter does, voxelize.gs:111-116);
+    // the entries of empty voxels are then stale until mat_normalize() writes -1 into them -- done lazily, before the grid is
+    // exposed (vt_read_volume) or scanned (vt_volume_assign_materials). Rendering, picking and editing read solid voxels only.
+    bool mat_stale_empties = false;
     unsigned long long* d_bricks_alloc = nullptr;         // padded array
     unsigned long long* d_bricks = nullptr;               // brick (0,0,0): d_bricks_alloc + 1 + PBX + PBX*PBY
     unsigned long long* d_bricks_empty = nullptr;         // template of the empty grid (sentinel shell only): clearing is one D2D copy
-    cudaStream_t aux_stream = nullptr; cudaEvent_t aux_fork = nullptr, aux_join = nullptr;   // side stream of vt_voxelize
     float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0}, vsize[3] = {0, 0, 0};
     // scene arrays
     float* d_materials = nullptr; size_t n_materials = 0;
@@ -181,9 +184,6 @@ void vt_destroy(vt_ctx* c)
     cudaFree(c->d_primary); cudaFree(c->d_work); cudaFree(c->d_shared); cudaFree(c->d_result); cudaFree(c->d_counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
-    if (c->aux_fork) cudaEventDestroy(c->aux_fork);
-    if (c->aux_join) cudaEventDestroy(c->aux_join);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -261,15 +261,25 @@ static int rebuild_dist(vt_ctx* c)
     return VT_OK;
 }
 
+static int mat_normalize(vt_ctx* c)
+{
+    if (!c->mat_stale_empties) return VT_OK;
+    vt_clear_empty_offsets_kernel<<<grid_for((size_t)c->BX * c->Y * c->Z, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_mat, c->X, c->Y, c->Z, c->BX, c->PBX, c->PBX * c->PBY);
+    c->launches += 1;
+    VT_CUDA(c, cudaGetLastError());
+    c->mat_stale_empties = false;
+    return VT_OK;
+}
+
 static int rebuild_occupancy(vt_ctx* c)
 {
+    c->mat_stale_empties = false;                      // the caller has just written the whole grid
     int rc = clear_occupancy(c);
     if (rc != VT_OK) return rc;
     const size_t rows = (size_t)c->BX * c->Y * c->Z;
     vt_build_bricks_kernel<<<grid_for(rows, 256), 256, 0, c->stream>>>(c->d_mat, c->d_bricks, c->X, c->Y, c->Z, c->BX, c->PBX, c->PBX * c->PBY);
     c->launches += 1;
-    rc = rebuild_dist(c);
-    if (rc != VT_OK) return rc;
+    c->dist_valid = false;                             // the renderer's distance field is rebuilt on its next use
     VT_CUDA(c, cudaGetLastError());
     return VT_OK;
 }
@@ -323,6 +333,7 @@ int vt_emissive_upload(vt_ctx* c, const int32_t* idx, size_t n)
     if (!c) return VT_ERR_INVALID;
     VT_REQ(c, idx || n == 0, "null emissive list");
     VT_BIND(c);
+    if (n > 0) { const int rc = mat_normalize(c); if (rc != VT_OK) return rc; }   // the list may name voxels that are empty
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
     c->n_emissive = n;
     return upload_array(c, (void**)&c->d_emissive, idx, n * sizeof(int32_t));
@@ -332,6 +343,7 @@ int vt_read_volume(vt_ctx* c, int32_t* out)
 {
     if (!c || !out) return VT_ERR_INVALID;
     VT_BIND(c);
+    { const int rc = mat_normalize(c); if (rc != VT_OK) return rc; }
     VT_CUDA(c, cudaMemcpyAsync(out, c->d_mat, sizeof(int32_t) * (size_t)c->X * c->Y * c->Z, cudaMemcpyDeviceToHost, c->stream));
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
     return VT_OK;
@@ -488,13 +500,18 @@ int vt_get_selection(vt_ctx* c, int32_t index[4], float normal[4])
 }
 
 // ---- launch parameter blocks ----------------------------------------------------------------------
+static bool skip_wanted(const vt_ctx* c)
+{
+    return c->skip_mode == 2 || (c->skip_mode == 1 && std::min(c->X, std::min(c->Y, c->Z)) >= 64);
+}
+
 static Volume make_volume(const vt_ctx* c)
 {
     Volume V;
     V.mat = c->d_mat; V.bricks = c->d_bricks;
     V.X = c->X; V.Y = c->Y; V.Z = c->Z;
     V.BX = c->PBX; V.BXY = c->PBX * c->PBY;               // strides of the padded brick array
-    const bool skip = c->dist_valid && (c->skip_mode == 2 || (c->skip_mode == 1 && std::min(c->X, std::min(c->Y, c->Z)) >= 64));
+    const bool skip = c->dist_valid && skip_wanted(c);
     V.dist = skip ? c->d_dist[c->dist_cur] : nullptr; V.CX = c->CX; V.CXY = c->CX * c->CY;
     V.bmin.x = c->bmin[0]; V.bmin.y = c->bmin[1]; V.bmin.z = c->bmin[2];
     V.bmax.x = c->bmax[0]; V.bmax.y = c->bmax[1]; V.bmax.z = c->bmax[2];
@@ -734,6 +751,7 @@ int vt_render(vt_ctx* c, int first_sample, int n_passes)
     const int tiles = L.tiles_x * L.tiles_y;
     const int my_tiles = (tiles - L.tile_rank + L.tile_world - 1) / L.tile_world;
     if (my_tiles > 0) {
+        if (!c->dist_valid && skip_wanted(c) && c->variant == 2) { const int rc = rebuild_dist(c); if (rc != VT_OK) return rc; }
         const Volume V = make_volume(c); const Frame F = make_frame(c);
         int* prim = c->primary_enabled ? c->d_primary : nullptr;
         if (c->variant == 2 && L.integrator == VT_INTEGRATOR_PATHTRACER) {
@@ -832,18 +850,7 @@ int vt_voxelize(vt_ctx* c, const float* xyz, size_t n_verts, const uint32_t* ind
     VT_CUDA(c, cudaMemcpyAsync(d_M, M, 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     const int n_tris = (int)(n_indices / 3);
     // timed region: clear + scatter + derive (kernel time incl. grid clear, excl. OBJ parse and H2D)
-    if (!c->aux_stream) {
-        VT_CUDA(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
-        VT_CUDA(c, cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
-        VT_CUDA(c, cudaEventCreateWithFlags(&c->aux_join, cudaEventDisableTiming));
-    }
     VT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    // the R32I grid is cleared to -1 by the copy engine path (HBM-write bound) on a side stream while the triangles are
-    // scattered into the bit grid (latency bound); the solid voxels' offsets are patched in afterwards
-    VT_CUDA(c, cudaEventRecord(c->aux_fork, c->stream));
-    VT_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->aux_fork, 0));
-    VT_CUDA(c, cudaMemsetAsync(c->d_mat, 0xff, sizeof(int32_t) * (size_t)X * Y * Z, c->aux_stream));
-    VT_CUDA(c, cudaEventRecord(c->aux_join, c->aux_stream));
     rc = clear_occupancy(c);
     if (rc != VT_OK) return rc;
     if (n_tris > 0) {
@@ -851,11 +858,12 @@ int vt_voxelize(vt_ctx* c, const float* xyz, size_t n_verts, const uint32_t* ind
         vt_voxelize_kernel<<<ctas, 128, 0, c->stream>>>(d_xyz, d_idx, n_tris, d_M, X, Y, Z, c->PBX, c->PBX * c->PBY, c->d_bricks);
         c->launches += 1;
     }
-    VT_CUDA(c, cudaStreamWaitEvent(c->stream, c->aux_join, 0));
+    // offsets of the solid voxels only; the stale entries of empty voxels are cleared lazily (mat_normalize)
     vt_fill_solid_kernel<<<grid_for((size_t)c->BX * c->BY * c->BZ, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_mat, X, Y, Z, c->BX, c->BY, c->BZ, c->PBX, c->PBX * c->PBY, fill);
     c->launches += 1;
-    rc = rebuild_dist(c);
-    if (rc != VT_OK) return rc;
+    c->dist_valid = false;                             // acceleration structure of the renderer: rebuilt on its next use
+    c->mat_stale_empties = true;
+    c->n_emissive = 0;                                  // the volume was replaced: the old emissive list refers to nothing
     VT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     VT_CUDA(c, cudaGetLastError());
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -874,6 +882,7 @@ int vt_volume_assign_materials(vt_ctx* c, const int32_t* table, int n_table, int
     int* d_table = nullptr;
     VT_CUDA(c, cudaMalloc(&d_table, n_table * sizeof(int)));
     VT_CUDA(c, cudaMemcpyAsync(d_table, table, n_table * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    { const int rc = mat_normalize(c); if (rc != VT_OK) return rc; }
     const size_t n = (size_t)c->X * c->Y * c->Z;
     vt_assign_materials_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->d_mat, c->X, c->Y, c->Z, d_table, n_table, rule);
     c->launches += 1;
@@ -917,8 +926,7 @@ int vt_add_voxel(vt_ctx* c, float mx, float my)
     vt_add_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), make_frame(c), mx, my, c->d_shared, c->d_mat, c->d_bricks, c->d_result);
     c->launches += 1;
     VT_CUDA(c, cudaGetLastError());
-    rc = rebuild_dist(c);                                   // an empty cell may have become solid
-    if (rc != VT_OK) return rc;
+    c->dist_valid = false;                                  // an empty cell may have become solid
     return VT_OK;
 }
 int vt_remove_voxel(vt_ctx* c)

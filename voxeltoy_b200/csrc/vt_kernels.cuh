@@ -147,7 +147,14 @@ __global__ void vt_add_voxel_kernel(const Volume V, const Frame F, float mx, flo
     const int cz = sh->sel_index[2] + f2i(normal.z);
     result[0] = 0; result[1] = cx; result[2] = cy; result[3] = cz;
     if ((unsigned)cx >= (unsigned)V.X || (unsigned)cy >= (unsigned)V.Y || (unsigned)cz >= (unsigned)V.Z) return;
-    int off = fetch_offset(V, sh->sel_index[0], sh->sel_index[1], sh->sel_index[2]);   // :37-40 (material of the selected voxel)
+    // :37-40 material of the selected voxel, the ground's (offset 0) when that voxel is empty. Emptiness is read from the
+    // occupancy bits: the offset entries of empty voxels may be stale (vt_voxelize)
+    const int sx = sh->sel_index[0], sy = sh->sel_index[1], sz = sh->sel_index[2];
+    int off = 0;
+    if ((unsigned)sx < (unsigned)V.X && (unsigned)sy < (unsigned)V.Y && (unsigned)sz < (unsigned)V.Z) {
+        const unsigned long long w = bricks[(sx >> 2) + (sy >> 2) * V.BX + (sz >> 2) * V.BXY];
+        if ((w >> ((sx & 3) | ((sy & 3) << 2) | ((sz & 3) << 4))) & 1ull) off = fetch_offset(V, sx, sy, sz);
+    }
     if (off < 0) off = 0;
     mat[(size_t)cx + (size_t)cy * V.X + (size_t)cz * V.X * V.Y] = off;
     set_voxel_bits(bricks, V, cx, cy, cz, true);
@@ -273,6 +280,22 @@ __global__ void vt_fill_offsets_kernel(const unsigned long long* __restrict__ br
         } else {
             for (int k = 0; k < 4; ++k) if ((bx << 2) + k < X) row[k] = ((m >> k) & 1u) ? fill : -1;
         }
+    }
+}
+
+// lazy counterpart of vt_fill_solid_kernel: writes -1 into every voxel whose occupancy bit is clear (one thread per x-run of 4)
+__global__ void vt_clear_empty_offsets_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
+                                              int X, int Y, int Z, int BX, int PBX, int BXY)
+{
+    const size_t n = (size_t)BX * (size_t)Y * (size_t)Z;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int bx = (int)(i % BX);
+        const size_t r = i / BX;
+        const int y = (int)(r % Y), z = (int)(r / Y);
+        const unsigned long long b = __ldg(bricks + ((long long)bx + (long long)(y >> 2) * PBX + (long long)(z >> 2) * BXY));
+        const unsigned int m = (unsigned int)(b >> (((y & 3) << 2) | ((z & 3) << 4))) & 0xfu;
+        int* row = mat + ((size_t)(bx << 2) + (size_t)y * X + (size_t)z * X * Y);
+        for (int k = 0; k < 4; ++k) if ((bx << 2) + k < X && !((m >> k) & 1u)) row[k] = -1;
     }
 }
 
