@@ -324,9 +324,13 @@ wf_trace_kernel(const Volume V, const WfState S, const WfBuf out, WfCounts* __re
         }
         if (__ballot_sync(full, have) == 0u) { if (exhausted) break; else continue; }
         // ---- the hot loop ----------------------------------------------------------------------------------
-        #pragma unroll
-        for (int k = 0; k < kWfStepChunk; ++k)
-            if (have && status == DDA_RUNNING) status = dda_step<COUNT>(V, s, tl);
+        if (have && status == DDA_RUNNING) {       // lanes leave the chunk through `break`: one reconvergence point per chunk, not per step
+            #pragma unroll
+            for (int k = 0; k < kWfStepChunk; ++k) {
+                status = dda_step<COUNT>(V, s, tl);
+                if (status != DDA_RUNNING) break;
+            }
+        }
         if (++chunks > chunk_guard && status == DDA_RUNNING) status = DDA_NOHIT;
         if (SKIP && !COUNT) {                     // counting builds step every voxel so that S stays the algorithmic count
             // the cheap part (one byte per lane) runs converged; the skip itself only when enough lanes want it, so that its
