@@ -679,6 +679,8 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
         VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, wf_shade_kernel<COUNT>, 128, 0));
         VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, wf_trace_kernel<COUNT, true>, 256, 0));
         VT_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        if (const char* e = getenv("VT_WF_SHADE_CTAS")) { const int v = atoi(e); if (v >= 1) per_sm_s = std::min(per_sm_s, v); }   // tuning knobs
+        if (const char* e = getenv("VT_WF_TRACE_CTAS")) { const int v = atoi(e); if (v >= 1) per_sm_t = std::min(per_sm_t, v); }
         c->wf_shade_blocks[ci] = std::max(1, per_sm_s) * std::max(1, sms);
         c->wf_trace_blocks[ci] = std::max(1, per_sm_t) * std::max(1, sms);
         c->wf_sms = std::max(1, sms);

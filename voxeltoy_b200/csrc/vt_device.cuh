@@ -227,7 +227,8 @@ VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
     const int key = (s.ix >> 2) + (s.iy >> 2) * V.BX + (s.iz >> 2) * V.BXY;
     if (key != s.bkey) { s.bkey = key; s.brick = __ldg(V.bricks + key); }
     const int bit = (s.ix & 3) | ((s.iy & 3) << 2) | ((s.iz & 3) << 4);
-    const unsigned int occ = (unsigned int)(s.brick >> bit);
+    unsigned int occ;      // low word of brick >> bit, kept opaque so that the test below stays a 32-bit one
+    asm("{ .reg .b64 t; shr.u64 t, %1, %2; cvt.u32.u64 %0, t; }" : "=r"(occ) : "l"(s.brick), "r"(bit));
     if (occ & 1u) {                                               // :44-50, or the voxel is outside: :41-42
         const bool inside = (unsigned)s.ix < (unsigned)V.X && (unsigned)s.iy < (unsigned)V.Y && (unsigned)s.iz < (unsigned)V.Z;
         if (inside) VT_TALLY(S, 1);
@@ -235,12 +236,26 @@ VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
     }
     VT_TALLY(S, 1);
     // :51 mask = step(dis.xyz, dis.yxy) * step(dis.xyz, dis.zzx)   (ties step several axes at once)
-    const bool mx = !(s.dy < s.dx) && !(s.dz < s.dx);
-    const bool my = !(s.dx < s.dy) && !(s.dz < s.dy);
-    const bool mz = !(s.dy < s.dz) && !(s.dx < s.dz);
-    if (mx) { s.dx = s.dx + s.ex; s.ix += s.sx; }                 // :52-53
-    if (my) { s.dy = s.dy + s.ey; s.iy += s.sy; }
-    if (mz) { s.dz = s.dz + s.ez; s.iz += s.sz; }
+    // Same arithmetic, instruction selection pinned: wf_trace is bound by the ALU pipe (78 % busy, profiles/r01_v6_*), so the
+    // axis masks are one 3-way minimum + three equality tests (an axis steps iff its dis IS the minimum: dis holds no NaN
+    // here, dda_begin) and the position updates are predicated multiply-adds, which issue on the FMA pipe.
+    asm volatile("{\n\t"
+                 ".reg .pred px, py, pz;\n\t"
+                 ".reg .f32 m;\n\t"
+                 "min.f32 m, %3, %4;\n\t"
+                 "min.f32 m, m, %5;\n\t"
+                 "setp.eq.f32 px, %3, m;\n\t"
+                 "setp.eq.f32 py, %4, m;\n\t"
+                 "setp.eq.f32 pz, %5, m;\n\t"
+                 "@px add.rn.f32 %3, %3, %6;\n\t"
+                 "@py add.rn.f32 %4, %4, %7;\n\t"
+                 "@pz add.rn.f32 %5, %5, %8;\n\t"
+                 "@px mad.lo.s32 %0, %9, 1, %0;\n\t"
+                 "@py mad.lo.s32 %1, %10, 1, %1;\n\t"
+                 "@pz mad.lo.s32 %2, %11, 1, %2;\n\t"
+                 "}"
+                 : "+r"(s.ix), "+r"(s.iy), "+r"(s.iz), "+f"(s.dx), "+f"(s.dy), "+f"(s.dz)
+                 : "f"(s.ex), "f"(s.ey), "f"(s.ez), "r"(s.sx), "r"(s.sy), "r"(s.sz));
     return DDA_RUNNING;                                           // :38,:55 the cap cannot be reached here, see dda_begin
 }
 
