@@ -256,8 +256,7 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
     if (valid) {
         out.ray0[slot] = make_float4(ro.x, ro.y, ro.z, rd.x);
         out.ray1[slot] = make_float4(rd.y, rd.z, 0.0f, i2f(0));
-        out.rad0[slot] = make_float4(0.f, 0.f, 0.f, 1.0f);
-        out.rad1[slot] = make_float4(1.0f, 1.0f, 0.f, 0.f);
+        // radiance 0, throughput 1, nothing pending: wf_shade synthesises rad0 / rad1 for primary paths instead of reading them
         out.rad2[slot] = make_float4(0.f, i2f(0), i2f(rng.x), i2f(rng.y));
         out.pid[slot] = pid;
         if (!want) out.hit[slot] = make_int4(s.ix, s.iy, s.iz, flags);
@@ -434,8 +433,9 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, 
         if (valid) {
             const unsigned int slot = qp[idx];
             pid = in.pid[slot];
-            const float4 r0 = in.ray0[slot], r1 = in.ray1[slot], a0 = in.rad0[slot];
             const int4 h = in.hit[slot];
+            const float4 r0 = in.ray0[slot], r1 = in.ray1[slot];
+            const float4 a0 = (h.w & WF_HIT_PRIMARY) ? make_float4(0.f, 0.f, 0.f, 1.0f) : in.rad0[slot];     // see wf_generate
             {   // gathers whose addresses are known now but whose values are needed hundreds of instructions later
                 const float4 a2p = in.rad2[slot];
                 const int nx = f2bits(a2p.z), ny = f2bits(a2p.w);
@@ -454,7 +454,7 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, 
                     radiance = background_color<COUNT>(F, rd, tl);
                     finished = true;
                 } else if (!(0 < F.max_bounces)) finished = true;                  // :214 never entered
-                if (!finished) { a1 = in.rad1[slot]; a2 = in.rad2[slot]; }
+                if (!finished) a2 = in.rad2[slot];                                 // a1 = throughput (1, 1), no pending light: the initialiser above
             } else {
                 a1 = in.rad1[slot]; a2 = in.rad2[slot];
                 // pathTracer.fs:248 with the shadow-ray result of the previous iteration
