@@ -269,8 +269,11 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
 // wf_trace: the loop of dda.h:38-57 for every ray record of the queue. Persistent warps; a warp reserves kWfGrab
 // rays per atomic and its lanes refill from that range whenever fewer than kWfLiveMin of them hold a ray.
 // ---------------------------------------------------------------------------------------------------------
+#ifndef VT_WF_TRACE_MIN_BLOCKS
+#define VT_WF_TRACE_MIN_BLOCKS 6
+#endif
 template <bool COUNT, bool SKIP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, VT_WF_TRACE_MIN_BLOCKS)
 wf_trace_kernel(const Volume V, const WfState S, const WfBuf out, WfCounts* __restrict__ cnt, Counters* __restrict__ counters)
 {
     const unsigned full = 0xffffffffu;
