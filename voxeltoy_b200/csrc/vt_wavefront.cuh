@@ -244,9 +244,15 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
         rng = rng_offset(px, py, sample, F.noise_w, F.noise_h);                    // :174
         generate_ray<COUNT>(F, frag, rng, ro, rd, tl);                             // :179
         const float t = ray_aabb(ro, rd, V.bmin, V.bmax);                          // :183
-        if (!(t < 0.0f)) {                                                         // else :187-194 -> finish queue
+        if (!(t < 0.0f)) {
             status = dda_begin<COUNT>(V, ro + t * rd, rd, s, tl);                  // :196-202
             if (status != DDA_RUNNING) flags = wf_hit_flags(status, s) | WF_HIT_PRIMARY;
+        } else {
+            // :187-194 the ray misses the volume's box: finished here. Such pixels come in whole 8x4 blocks (the sky), so the
+            // warp does not diverge, and the path never costs a slot, a queue entry or a pass through wf_shade.
+            const f3 c = tonemap(background_color<COUNT>(F, rd, tl));
+            S.samples[pid] = make_float4(c.x, c.y, c.z, 1.0f);
+            valid = false;
         }
         if (primary != nullptr && pass0 + pass_local == L.n_passes - 1) primary[(size_t)px + (size_t)py * (size_t)F.W] = -1;
     }
