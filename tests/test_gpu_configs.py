@@ -173,3 +173,54 @@ def test_advance_until_closed_form_equals_literal_loop(vt_ctx):
     assert np.array_equal(a_k, b_k), "%d counts differ" % int((a_k != b_k).sum())
     assert np.array_equal(a_d.view(np.uint32), b_d.view(np.uint32))
     assert (a_k > 50).sum() > 10000 and (a_k == nmax).sum() > 1000 and (a_k == 0).sum() > 100
+
+
+def test_full_size_properties_c3_c4(vt_ctx):
+    """BASELINE configs 3 and 4 at their FULL sizes, through size-independent properties (the oracle is too slow here):
+    C3: re-voxelizing bunny.obj at 512^3 is idempotent, the occupancy equals the set of written offsets, the shell is thin
+    (every solid voxel has an empty 6-neighbour) and 8x the 64^3 surface area within 25 %;
+    C4: 256^3 terrain at 3840x2160, 8 bounces: the union of an 8-way tile partition equals the full frame bit for bit,
+    and the wavefront renderer equals the megakernel bit for bit."""
+    verts, idx = oscene.load_obj(util.BUNNY)
+    bmin, bmax = oscene.mesh_bounds(verts)
+    res = (512, 512, 512)
+    M = oscene.mesh_transform(bmin, bmax, res)
+    vt_ctx.voxelize(verts, idx, M, res, fill_offset=3)
+    a = vt_ctx.read_volume()
+    vt_ctx.voxelize(verts, idx, M, res, fill_offset=3)
+    b = vt_ctx.read_volume()
+    assert np.array_equal(a, b) and set(np.unique(a)) == {-1, 3}
+    solid = (a >= 0).reshape(512, 512, 512)
+    n512 = int(solid.sum())
+    inner = solid[1:-1, 1:-1, 1:-1] & solid[:-2, 1:-1, 1:-1] & solid[2:, 1:-1, 1:-1] & solid[1:-1, :-2, 1:-1] & solid[1:-1, 2:, 1:-1] \
+        & solid[1:-1, 1:-1, :-2] & solid[1:-1, 1:-1, 2:]
+    assert int(inner.sum()) < n512 // 50                      # a surface shell, not a filled solid
+    M64 = oscene.mesh_transform(bmin, bmax, (64, 64, 64))
+    n64 = int((vto.voxelize(verts, idx, M64, (64, 64, 64)) > 0).sum())
+    assert 0.75 < n512 / (64.0 * n64) < 1.25                  # area scales with the square of the resolution
+    del a, b, solid, inner
+
+    n = 256
+    ids = scenes.terrain_grid(n)
+    t = scenes.MaterialTable()
+    t.lambert((0.55, 0.5, 0.45)); t.metal((0.8, 0.8, 0.85), 60.0); t.lambert((0.3, 0.1, 0.05), emission=(6.0, 2.0, 0.5))
+    grid = scenes.ids_to_offsets(ids, t.offsets); mats = t.array()
+    em = oscene.prune_interior_emissive(grid, (n, n, n), scenes.emissive_list(grid, mats))
+    d = util.make_frame(dict(res=(n, n, n), grid=grid, materials=mats, emissive=em), 3840, 2160, bounces=8, theta=140, phi=35)
+    util.upload(vt_ctx, d)
+    vt_ctx.render(0, 2)
+    full = vt_ctx.read_average()
+    acc = np.zeros_like(full)
+    for r in range(8):
+        util.upload(vt_ctx, d)
+        vt_ctx.set_partition(vt.VT_PART_TILES, r, 8)
+        vt_ctx.render(0, 2)
+        acc += vt_ctx.read_average()
+    vt_ctx.set_partition(vt.VT_PART_NONE, 0, 1)
+    assert util.same_bits(acc, full).all()
+    util.upload(vt_ctx, d)
+    vt_ctx.set_kernel_variant(0)
+    vt_ctx.render(0, 2)
+    mega = vt_ctx.read_average()
+    vt_ctx.set_kernel_variant(2)
+    assert util.same_bits(mega, full).all()
