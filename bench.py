@@ -329,6 +329,20 @@ def main():
             r2.close()
         except Exception as e:
             line["voxelize"] = {"metric": "voxelize ms @512^3", "value": None, "error": repr(e)}
+        # environment ingest (RGBA conversion, importance function, CDFs, integral) on the device vs the
+        # same chain on one host core (host/image.cpp calculateCDF, the reference's renderer/image.cpp:68-389)
+        try:
+            c3 = vt.Context(local_rank)
+            env_rgb = vt.scenes.synthetic_env(1024, 512)
+            ems = []
+            for _ in range(4):
+                c3.env_build(env_rgb); ems.append(c3.env_info()["build_ms"])
+            t0 = time.perf_counter(); vt.host.calculate_cdf(env_rgb); host_ms = (time.perf_counter() - t0) * 1e3
+            line["env_build"] = {"metric": "env ingest ms (1024x512 RGB -> RGBA + 512x256 CDFs)", "value": min(ems), "unit": "ms",
+                                 "runs_ms": ems, "host_calculateCDF_ms_1_core": host_ms}
+            c3.close()
+        except Exception as e:
+            line["env_build"] = {"value": None, "error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r = cpu_reference_run(steps=2, warmup=1)

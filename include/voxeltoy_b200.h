@@ -113,6 +113,17 @@ int vt_env_upload(vt_ctx* ctx, const float* rgb, int w, int h,
                   const float* cdf_u, int cdf_u_w, int cdf_u_h,
                   const float* cdf_v, int cdf_v_n, float integral);
 int vt_env_clear(vt_ctx* ctx);
+/* The processing half of Renderer::loadBackgroundImage on the device (renderer.cpp:947-1055 + renderer/image.cpp:68-389:
+ * RGBA conversion, <= 512 box reduction, luminance, 3x3 gaussian, sin(theta) weights, integral, CDF-U / CDF-V):
+ * the caller passes the decoded RGB float image (row 0 = first scanline of the file, as OIIO delivers it) and gets the
+ * state vt_env_upload would have set from the host-built arrays, bit for bit. Fails (VT_ERR_INVALID) like
+ * calculateCDF when the image cannot be box-reduced by integer factors. */
+int vt_env_build(vt_ctx* ctx, const float* rgb, int w, int h);
+/* dims[6] = {env w, env h, CDF-U width, CDF-U height, CDF-V length, guide tables in use}; *integral = the uniform
+ * backgroundIntegral (renderer.cpp:1048-1052); *build_ms = device time of the last vt_env_build. Any pointer may be NULL. */
+int vt_get_env_info(vt_ctx* ctx, int32_t* dims, float* integral, float* build_ms);
+/* read back the CDF textures (sizes from vt_get_env_info); either pointer may be NULL */
+int vt_read_env_cdf(vt_ctx* ctx, float* cdf_u, float* cdf_v);
 
 /* ---- per-frame state -------------------------------------------------------------- */
 int vt_set_camera(vt_ctx* ctx, const vt_camera* cam);       /* updateCamera, renderer.cpp:410-444 */

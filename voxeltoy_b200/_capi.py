@@ -53,6 +53,9 @@ SIGNATURES = {
     "vt_noise_upload": (C.c_int, [P, f32p, C.c_int, C.c_int]),
     "vt_env_upload": (C.c_int, [P, f32p, C.c_int, C.c_int, f32p, C.c_int, C.c_int, f32p, C.c_int, C.c_float]),
     "vt_env_clear": (C.c_int, [P]),
+    "vt_env_build": (C.c_int, [P, f32p, C.c_int, C.c_int]),
+    "vt_get_env_info": (C.c_int, [P, i32p, f32p, f32p]),
+    "vt_read_env_cdf": (C.c_int, [P, f32p, f32p]),
     "vt_set_camera": (C.c_int, [P, C.POINTER(VtCamera)]),
     "vt_set_settings": (C.c_int, [P, C.POINTER(VtSettings)]),
     "vt_set_focal_distance": (C.c_int, [P, C.c_float]),
@@ -183,6 +186,24 @@ class Context:
         cv = np.ascontiguousarray(cdf_v, np.float32)
         self._ck(self.lib.vt_env_upload(self.h, _fp(rgb), rgb.shape[1], rgb.shape[0], _fp(cu), cu.shape[1], cu.shape[0],
                                         _fp(cv), cv.size, float(integral)))
+
+    def env_build(self, rgb):
+        """vt_env_build: RGB float image (h, w, 3) -> env texture + CDFs + integral, all on the device"""
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        assert rgb.ndim == 3 and rgb.shape[2] == 3
+        self._ck(self.lib.vt_env_build(self.h, _fp(rgb), rgb.shape[1], rgb.shape[0]))
+
+    def env_info(self):
+        dims = np.zeros(6, np.int32); integral = C.c_float(0); ms = C.c_float(0)
+        self._ck(self.lib.vt_get_env_info(self.h, _ip(dims), C.cast(C.byref(integral), f32p), C.cast(C.byref(ms), f32p)))
+        return dict(w=int(dims[0]), h=int(dims[1]), cdf_u_w=int(dims[2]), cdf_u_h=int(dims[3]), cdf_v_n=int(dims[4]), guided=bool(dims[5]),
+                    integral=float(integral.value), build_ms=float(ms.value))
+
+    def read_env_cdf(self):
+        i = self.env_info()
+        cu = np.empty((i["cdf_u_h"], i["cdf_u_w"]), np.float32); cv = np.empty(i["cdf_v_n"], np.float32)
+        self._ck(self.lib.vt_read_env_cdf(self.h, _fp(cu), _fp(cv)))
+        return cu, cv
 
     def env_clear(self):
         self._ck(self.lib.vt_env_clear(self.h))

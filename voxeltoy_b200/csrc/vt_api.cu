@@ -5,6 +5,7 @@
 #include "../../include/voxeltoy_b200.h"
 #include "vt_pathstate.cuh"
 #include "vt_wavefront.cuh"
+#include "vt_env.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -81,7 +82,7 @@ struct vt_ctx {
     Counters* d_counters = nullptr; bool count_enabled = false;
     uint64_t paths = 0, launches = 0;
     // voxelizer timing
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr; float last_voxelize_ms = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr; float last_voxelize_ms = 0.f, last_env_build_ms = 0.f;
 };
 
 static int fail(vt_ctx* c, int code, const char* fmt, ...)
@@ -438,6 +439,100 @@ int vt_env_clear(vt_ctx* c)
     c->d_guide_v = nullptr; c->d_guide_u = nullptr; c->guide_k = 0;
     c->d_env = nullptr; c->d_cdf_u = nullptr; c->d_cdf_v = nullptr;
     c->env_w = c->env_h = c->cdf_u_w = c->cdf_u_h = c->cdf_v_n = 0; c->env_integral = 0.f;
+    return VT_OK;
+}
+
+
+// Renderer::loadBackgroundImage's processing half on the device (kernels in vt_env.cuh): the
+// caller hands over the decoded RGB float image only. Same results, bit for bit, as calculateCDF of
+// voxeltoy_b200/host/image.cpp (= image.cpp:68-389 of the reference) followed by vt_env_upload.
+int vt_env_build(vt_ctx* c, const float* rgb, int w, int h)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, rgb && w > 0 && h > 0 && w <= 16384 && h <= 16384, "bad environment image");
+    int nw = w, nh = h, fx = 1, fy = 1;
+    const int m = std::max(w, h);
+    if (m > VT_ENV_MAX_CDF_SIZE) {                                     // image.cpp:309-321: box filter needs integer factors
+        nw = (int)((float)w / m * VT_ENV_MAX_CDF_SIZE); nh = (int)((float)h / m * VT_ENV_MAX_CDF_SIZE);
+        VT_REQ(c, nw > 0 && nh > 0, "environment image too elongated for the CDF size limit");
+        fx = w / nw; fy = h / nh;
+        VT_REQ(c, fx * nw == w && fy * nh == h, "environment image size must be an integer multiple of its <= 512 reduction");
+    }
+    VT_BIND(c);
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    vt_env_clear(c);
+    const size_t npx = (size_t)w * h, ncdf = (size_t)nw * nh;
+    std::vector<float> sin_row(nh);
+    for (int y = 0; y < nh; ++y) sin_row[y] = (float)sin(M_PI * ((float)y + 0.5f) / (float)nh);     // image.cpp:366
+    float *d_rgb = nullptr, *d_a = nullptr, *d_b = nullptr, *d_sin = nullptr, *d_fv = nullptr, *d_out = nullptr;
+    int* d_sorted = nullptr;
+    const int K = 256;
+    auto cleanup = [&]() { cudaFree(d_rgb); cudaFree(d_a); cudaFree(d_b); cudaFree(d_sin); cudaFree(d_fv); cudaFree(d_out); cudaFree(d_sorted); };
+#define VT_ENV_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); vt_env_clear(c); \
+        return fail(c, VT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    VT_ENV_CUDA(cudaMalloc(&d_rgb, npx * 3 * sizeof(float)));
+    VT_ENV_CUDA(cudaMalloc(&d_a, ncdf * sizeof(float)));
+    VT_ENV_CUDA(cudaMalloc(&d_b, ncdf * sizeof(float)));
+    VT_ENV_CUDA(cudaMalloc(&d_sin, nh * sizeof(float)));
+    VT_ENV_CUDA(cudaMalloc(&d_fv, nh * sizeof(float)));
+    VT_ENV_CUDA(cudaMalloc(&d_out, sizeof(float)));
+    VT_ENV_CUDA(cudaMalloc(&d_sorted, sizeof(int)));
+    VT_ENV_CUDA(cudaMalloc(&c->d_env, npx * sizeof(float4)));
+    VT_ENV_CUDA(cudaMalloc(&c->d_cdf_u, (size_t)(nw + 1) * nh * sizeof(float)));
+    VT_ENV_CUDA(cudaMalloc(&c->d_cdf_v, (size_t)(nh + 1) * sizeof(float)));
+    VT_ENV_CUDA(cudaMalloc(&c->d_guide_v, (size_t)(K + 1) * sizeof(unsigned short)));
+    VT_ENV_CUDA(cudaMalloc(&c->d_guide_u, (size_t)nh * (K + 1) * sizeof(unsigned short)));
+    cudaStream_t st = c->stream;
+    const int one = 1;
+    VT_ENV_CUDA(cudaMemcpyAsync(d_rgb, rgb, npx * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    VT_ENV_CUDA(cudaMemcpyAsync(d_sin, sin_row.data(), nh * sizeof(float), cudaMemcpyHostToDevice, st));
+    VT_ENV_CUDA(cudaMemcpyAsync(d_sorted, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    VT_ENV_CUDA(cudaEventRecord(c->ev0, st));
+    const dim3 g2((nw + 127) / 128, nh);
+    vt_env_rgba_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(d_rgb, c->d_env, npx);
+    vt_env_luminance_kernel<<<g2, 128, 0, st>>>(d_rgb, w, nw, nh, fx, fy, d_a);
+    vt_env_blur_kernel<<<g2, 128, 0, st>>>(d_a, d_b, nw, nh, 0);
+    vt_env_blur_kernel<<<g2, 128, 0, st>>>(d_b, d_a, nw, nh, 1);
+    vt_env_function_kernel<<<g2, 128, 0, st>>>(d_a, d_sin, nw, nh, d_b);
+    vt_env_sum_kernel<<<1, 256, 0, st>>>(d_b, ncdf, d_out);
+    vt_env_cdf_rows_kernel<<<(nh + 3) / 4, 128, 0, st>>>(d_b, nw, nh, c->d_cdf_u, d_fv);
+    vt_env_cdf_v_kernel<<<1, 32, 0, st>>>(d_fv, nh, c->d_cdf_v);
+    vt_env_guide_kernel<<<1, 128, 0, st>>>(c->d_cdf_v, nh + 1, 0, 1, K, c->d_guide_v, d_sorted);
+    vt_env_guide_kernel<<<nh, 128, 0, st>>>(c->d_cdf_u, nw + 1, nw + 1, nh, K, c->d_guide_u, d_sorted);
+    VT_ENV_CUDA(cudaGetLastError());
+    VT_ENV_CUDA(cudaEventRecord(c->ev1, st));
+    float sum = 0.f; int sorted = 0;
+    VT_ENV_CUDA(cudaMemcpyAsync(&sum, d_out, sizeof(float), cudaMemcpyDeviceToHost, st));
+    VT_ENV_CUDA(cudaMemcpyAsync(&sorted, d_sorted, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VT_ENV_CUDA(cudaStreamSynchronize(st));
+    VT_ENV_CUDA(cudaEventElapsedTime(&c->last_env_build_ms, c->ev0, c->ev1));
+#undef VT_ENV_CUDA
+    cleanup();
+    float integral = sum / ((float)nw * (float)nh);                      // image.cpp:381-386 (float * double constants)
+    integral = (float)((double)integral * (2.0f * M_PI * M_PI));
+    c->env_w = w; c->env_h = h; c->cdf_u_w = nw + 1; c->cdf_u_h = nh; c->cdf_v_n = nh + 1; c->env_integral = integral;
+    if (sorted && nw - 1 <= 65535 && nh - 1 <= 65535) c->guide_k = K;
+    else { cudaFree(c->d_guide_v); cudaFree(c->d_guide_u); c->d_guide_v = nullptr; c->d_guide_u = nullptr; c->guide_k = 0; }
+    return VT_OK;
+}
+
+int vt_get_env_info(vt_ctx* c, int32_t* dims /* w, h, cdf_u_w, cdf_u_h, cdf_v_n, guided */, float* integral, float* build_ms)
+{
+    if (!c) return VT_ERR_INVALID;
+    if (build_ms) *build_ms = c->last_env_build_ms;
+    if (dims) { dims[0] = c->env_w; dims[1] = c->env_h; dims[2] = c->cdf_u_w; dims[3] = c->cdf_u_h; dims[4] = c->cdf_v_n; dims[5] = c->guide_k > 0; }
+    if (integral) *integral = c->env_integral;
+    return VT_OK;
+}
+
+int vt_read_env_cdf(vt_ctx* c, float* cdf_u, float* cdf_v)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, c->d_cdf_u && c->d_cdf_v, "no environment map loaded");
+    VT_BIND(c);
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (cdf_u) VT_CUDA(c, cudaMemcpy(cdf_u, c->d_cdf_u, sizeof(float) * (size_t)c->cdf_u_w * c->cdf_u_h, cudaMemcpyDeviceToHost));
+    if (cdf_v) VT_CUDA(c, cudaMemcpy(cdf_v, c->d_cdf_v, sizeof(float) * (size_t)c->cdf_v_n, cudaMemcpyDeviceToHost));
     return VT_OK;
 }
 

@@ -259,12 +259,10 @@ bool Renderer::loadBackgroundImage(float& mapIntegralTimesSin)                  
         log("Background image loading failed: " + m_renderSettings.m_backgroundImage);
         return false;
     }
-    unsigned int cw, ch;
-    std::vector<float> cdfU, cdfV;
-    float integral;
-    if (!calculateCDF(&pixels[0], w, h, cdfU, cw, ch, cdfV, integral)) { log("Background CDF construction failed"); return false; }
-    if (vt_env_upload(m_ctx, &pixels[0], (int)w, (int)h, &cdfU[0], (int)cw, (int)ch, &cdfV[0], (int)cdfV.size(), integral) != VT_OK) {
-        m_status = vt_last_error(m_ctx); return false;
+    // renderer.cpp:1004-1046 + image.cpp:68-389 (importance function, CDFs, integral) run on the device: vt_env_build
+    float integral = 0;
+    if (vt_env_build(m_ctx, &pixels[0], (int)w, (int)h) != VT_OK || vt_get_env_info(m_ctx, NULL, &integral, NULL) != VT_OK) {
+        m_status = vt_last_error(m_ctx); log("Background CDF construction failed: " + m_status); return false;
     }
     mapIntegralTimesSin = integral;
     m_currentBackgroundImage = m_renderSettings.m_backgroundImage;
