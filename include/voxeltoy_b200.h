@@ -141,6 +141,9 @@ int vt_reset_accumulation(vt_ctx* ctx);                     /* resetRender, rend
 int vt_render(vt_ctx* ctx, int first_sample, int n_passes);
 int vt_get_num_samples(vt_ctx* ctx, int* n);                /* m_numberSamples */
 int vt_read_average(vt_ctx* ctx, float* rgba_out);          /* glGetTexImage(average), renderer.cpp:1119-1127 */
+/* the display blit (shared/textureMap.fs, renderer.cpp:613-637) as a read-out: W*H RGBA8, float -> UNORM8 as a GL
+ * framebuffer write does it; flip_vertical != 0 gives top-down rows (saveImage's order, renderer.cpp:1131-1136) */
+int vt_read_display(vt_ctx* ctx, uint8_t* rgba8_out, int flip_vertical);
 int vt_read_primary_hits(vt_ctx* ctx, int32_t* out);        /* per pixel: linear voxel index, -1 miss, -2 ground (last pass) */
 int vt_enable_primary_hits(vt_ctx* ctx, int enable);
 /* multi-GPU: restrict this context to its share of the frame (tiles: 64x64 tiles dealt round-robin, result bit-identical

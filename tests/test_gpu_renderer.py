@@ -87,6 +87,18 @@ def test_renderer_c2_flow_env_thin_lens_autofocus(renderer, tmp_path):
     out = str(tmp_path / "o.pfm")
     r.saveImage(out)
     assert util.same_bits(vt.host.load_image(out)[::-1], got[..., :3]).all()
+    # 8-bit export = the display blit (textureMap.fs) as a read-out: GL float -> UNORM8 conversion on the device, top row first
+    from tests.test_host_parity import _decode_png
+    want = np.rint(np.clip(np.nan_to_num(got, nan=0.0), 0.0, 1.0) * np.float32(255.0)).astype(np.uint8)
+    assert np.array_equal(r.context().read_display(), want)
+    png = str(tmp_path / "o.png")
+    r.saveImage(png)
+    assert np.array_equal(_decode_png(png), want[::-1])
+    ppm = str(tmp_path / "o.ppm")
+    r.saveImage(ppm)
+    raw = open(ppm, "rb").read()
+    head = b"P6\n240 136\n255\n"
+    assert raw.startswith(head) and np.array_equal(np.frombuffer(raw[len(head):], np.uint8).reshape(136, 240, 3), want[::-1, :, :3])
 
 
 def test_renderer_mesh_tools_and_edit_flow(renderer):

@@ -118,3 +118,32 @@ def test_image_file_readers(host, tmp_path):
     assert np.allclose(got, px, rtol=0.02, atol=1e-4)
     with pytest.raises(IOError):
         host.load_image(str(tmp_path / "nope.hdr"))
+
+
+def _decode_png(path):
+    """minimal PNG reader for the test: checks signature and chunk CRCs, inflates IDAT with zlib, expects filter 0 rows"""
+    import struct
+    import zlib
+    b = open(path, "rb").read()
+    assert b[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, chunks = 8, []
+    while pos < len(b):
+        n, typ = struct.unpack(">I4s", b[pos:pos + 8])
+        data = b[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", b[pos + 8 + n:pos + 12 + n])[0] == (zlib.crc32(typ + data) & 0xFFFFFFFF)
+        chunks.append((typ, data)); pos += 12 + n
+    assert [c[0] for c in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+    w, h, depth, ctype, comp, flt, lace = struct.unpack(">IIBBBBB", chunks[0][1])
+    assert (depth, ctype, comp, flt, lace) == (8, 6, 0, 0, 0)
+    raw = np.frombuffer(zlib.decompress(chunks[1][1]), np.uint8).reshape(h, 1 + 4 * w)
+    assert not raw[:, 0].any()
+    return raw[:, 1:].reshape(h, w, 4)
+
+
+def test_png_writer_round_trip(host, tmp_path):
+    rng = np.random.default_rng(3)
+    for (h, w) in ((1, 1), (7, 5), (300, 257)):            # the last one spans several 65535-byte stored blocks
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        p = str(tmp_path / ("t%dx%d.png" % (w, h)))
+        host.write_png(p, img)
+        assert np.array_equal(_decode_png(p), img)

@@ -65,6 +65,7 @@ SIGNATURES = {
     "vt_reset_accumulation": (C.c_int, [P]),
     "vt_render": (C.c_int, [P, C.c_int, C.c_int]),
     "vt_get_num_samples": (C.c_int, [P, C.POINTER(C.c_int)]),
+    "vt_read_display": (C.c_int, [P, C.c_void_p, C.c_int]),
     "vt_read_average": (C.c_int, [P, f32p]),
     "vt_read_primary_hits": (C.c_int, [P, i32p]),
     "vt_enable_primary_hits": (C.c_int, [P, C.c_int]),
@@ -286,6 +287,13 @@ class Context:
         if out is None:
             out = np.empty((self.height, self.width, 4), np.float32)
         self._ck(self.lib.vt_read_average(self.h, _fp(out)))
+        return out
+
+    def read_display(self, flip_vertical=False, out=None):
+        """vt_read_display: the average as RGBA8 (GL float -> UNORM8 conversion), optionally in top-down row order"""
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.uint8)
+        self._ck(self.lib.vt_read_display(self.h, out.ctypes.data_as(C.c_void_p), int(bool(flip_vertical))))
         return out
 
     def enable_primary_hits(self, on=True):

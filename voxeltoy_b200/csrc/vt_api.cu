@@ -54,6 +54,7 @@ struct vt_ctx {
     vt_settings st{};
     bool have_cam = false, have_settings = false;
     float4* d_accum = nullptr; size_t accum_pixels = 0;
+    uchar4* d_display = nullptr;                          // RGBA8 display image (vt_read_display), allocated on first use
     int32_t* d_primary = nullptr; bool primary_enabled = false;
     int num_samples = 0;
     Shared* d_shared = nullptr;
@@ -171,7 +172,7 @@ void vt_destroy(vt_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_bricks_empty); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]); cudaFree(c->d_materials); cudaFree(c->d_emissive);
-    cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum);
+    cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum); cudaFree(c->d_display);
     cudaFree(c->d_guide_v); cudaFree(c->d_guide_u);
     for (int k = 0; k < vt_ctx::kWfLanes; ++k) {
         cudaFree(c->d_wf_pool[k]); cudaFree(c->d_wf_counts[k]);
@@ -548,7 +549,7 @@ int vt_set_settings(vt_ctx* c, const vt_settings* st)
     const size_t px = (size_t)st->width * st->height;
     if (px != c->accum_pixels || st->width != c->st.width || !c->d_accum) {
         VT_CUDA(c, cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_accum); cudaFree(c->d_primary); c->d_accum = nullptr; c->d_primary = nullptr;
+        cudaFree(c->d_accum); cudaFree(c->d_primary); cudaFree(c->d_display); c->d_accum = nullptr; c->d_primary = nullptr; c->d_display = nullptr;
         VT_CUDA(c, cudaMalloc(&c->d_accum, px * sizeof(float4)));
         VT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, px * sizeof(float4), c->stream));
         c->accum_pixels = px;
@@ -901,6 +902,23 @@ int vt_read_primary_hits(vt_ctx* c, int32_t* out)
     if (!c->d_primary) return fail(c, VT_ERR_STATE, "primary hits not enabled before the last vt_render");
     VT_BIND(c);
     VT_CUDA(c, cudaMemcpyAsync(out, c->d_primary, c->accum_pixels * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VT_OK;
+}
+
+// K3 (shared/textureMap.fs + the blit of renderer.cpp:613-637) as a read-out: the running average converted the way GL
+// converts a float colour written to an 8-bit UNORM framebuffer (clamp to [0, 1], scale by 255, round to nearest; NaN -> 0),
+// optionally flipped to top-down row order for image files (saveImage's negative stride, renderer.cpp:1131-1136).
+int vt_read_display(vt_ctx* c, uint8_t* rgba8_out, int flip_vertical)
+{
+    if (!c || !rgba8_out) return VT_ERR_INVALID;
+    if (!c->d_accum) return fail(c, VT_ERR_STATE, "no frame");
+    VT_BIND(c);
+    if (!c->d_display) VT_CUDA(c, cudaMalloc(&c->d_display, c->accum_pixels * sizeof(uchar4)));
+    const int W = c->st.width, H = c->st.height;
+    vt_display_kernel<<<(unsigned)((c->accum_pixels + 255) / 256), 256, 0, c->stream>>>(c->d_accum, c->d_display, W, H, flip_vertical ? 1 : 0);
+    VT_CUDA(c, cudaGetLastError());
+    VT_CUDA(c, cudaMemcpyAsync(rgba8_out, c->d_display, c->accum_pixels * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
     return VT_OK;
 }

@@ -468,4 +468,17 @@ __global__ void vt_trace_rays_kernel(const Volume V, const float* __restrict__ r
     out[4 * i + 3] = h ? (g ? 2.0f : 1.0f) : 0.0f;
 }
 
+// K3: the display blit (shared/textureMap.fs:8-11 samples the average texture 1:1 into the default framebuffer). Float ->
+// 8-bit UNORM as GL does it on a framebuffer write: clamp to [0, 1] (NaN -> 0), * 255, round to nearest even.
+__device__ __forceinline__ unsigned char unorm8(float v) { return (unsigned char)__float2int_rn(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f); }
+
+__global__ void vt_display_kernel(const float4* __restrict__ avg, uchar4* __restrict__ out, int W, int H, int flip)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)W * H) return;
+    const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+    const float4 c = avg[i];
+    out[(size_t)(flip ? H - 1 - y : y) * W + x] = make_uchar4(unorm8(c.x), unorm8(c.y), unorm8(c.z), unorm8(c.w));
+}
+
 } // namespace vt

@@ -65,6 +65,7 @@ _SIG = {
     "vth_cdf_dims": (None, [P, C.POINTER(C.c_uint), C.POINTER(C.c_uint), f32p]),
     "vth_cdf_copy": (None, [P, f32p, f32p]), "vth_cdf_free": (None, [P]),
     "vth_write_pfm": (C.c_int, [C.c_char_p, f32p, C.c_uint, C.c_uint]),
+    "vth_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint, C.c_uint]),
     "vth_load_image_dims": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "vth_load_image": (C.c_int, [C.c_char_p, f32p]),
 }
@@ -170,6 +171,14 @@ def calculate_cdf(rgb):
     finally:
         L.vth_cdf_free(h)
     return dict(rgb=rgb, cdf_u=cu, cdf_v=cv, integral=float(integral.value))
+
+
+def write_png(path, rgba8):
+    """writePNG (host/image.cpp): (h, w, 4) uint8, rows top-down"""
+    rgba8 = np.ascontiguousarray(rgba8, np.uint8)
+    assert rgba8.ndim == 3 and rgba8.shape[2] == 4
+    if lib().vth_write_png(path.encode(), rgba8.ctypes.data_as(C.c_void_p), rgba8.shape[1], rgba8.shape[0]) != 0:
+        raise IOError("cannot write " + path)
 
 
 def write_pfm(path, rgb):

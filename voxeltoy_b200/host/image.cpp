@@ -99,6 +99,62 @@ bool writePFM(const std::string& path, const float* rgb, unsigned int w, unsigne
     return true;
 }
 
+// ---- PNG (RGBA8, rows top-down) ------------------------------------------------------------------------------------------
+// The reference writes whatever format OpenImageIO derives from the file extension (renderer.cpp:1129-1138); PNG is what its
+// UI offers. A PNG is a zlib stream inside IDAT; this writer emits *stored* deflate blocks (no compression, no dependency):
+// every decoder accepts them. CRC-32 (ISO 3309) over chunk type + data, Adler-32 over the raw scanlines.
+static uint32_t crc32_update(uint32_t crc, const unsigned char* p, size_t n)
+{
+    static uint32_t table[256]; static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+        init = true;
+    }
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xFF] ^ (crc >> 8);
+    return crc;
+}
+
+static void put_be32(std::vector<unsigned char>& v, uint32_t x) { v.push_back(x >> 24); v.push_back((x >> 16) & 0xFF); v.push_back((x >> 8) & 0xFF); v.push_back(x & 0xFF); }
+
+static bool write_chunk(FILE* fp, const char type[4], const std::vector<unsigned char>& data)
+{
+    std::vector<unsigned char> head; put_be32(head, (uint32_t)data.size());
+    uint32_t crc = crc32_update(0xFFFFFFFFu, (const unsigned char*)type, 4);
+    if (!data.empty()) crc = crc32_update(crc, &data[0], data.size());
+    std::vector<unsigned char> tail; put_be32(tail, crc ^ 0xFFFFFFFFu);
+    return fwrite(&head[0], 1, 4, fp) == 4 && fwrite(type, 1, 4, fp) == 4 && (data.empty() || fwrite(&data[0], 1, data.size(), fp) == data.size())
+        && fwrite(&tail[0], 1, 4, fp) == 4;
+}
+
+bool writePNG(const std::string& path, const unsigned char* rgba8, unsigned int w, unsigned int h)
+{
+    if (!rgba8 || w == 0 || h == 0) return false;
+    FILE* fp = fopen(path.c_str(), "wb");
+    if (!fp) return false;
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    bool ok = fwrite(sig, 1, 8, fp) == 8;
+    std::vector<unsigned char> ihdr; put_be32(ihdr, w); put_be32(ihdr, h);
+    ihdr.push_back(8); ihdr.push_back(6); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);   // 8 bit, RGBA, deflate, filter 0, no interlace
+    ok = ok && write_chunk(fp, "IHDR", ihdr);
+    const size_t stride = (size_t)w * 4 + 1, rawSize = stride * h;                                   // filter byte 0 (None) per scanline
+    std::vector<unsigned char> raw(rawSize);
+    for (unsigned int y = 0; y < h; ++y) { raw[y * stride] = 0; memcpy(&raw[y * stride + 1], rgba8 + (size_t)y * w * 4, (size_t)w * 4); }
+    uint32_t a = 1, b = 0;                                                                           // Adler-32, deferred modulo (5552 bytes)
+    for (size_t i = 0; i < rawSize;) { const size_t n = std::min<size_t>(5552, rawSize - i); for (size_t k = 0; k < n; ++k) { a += raw[i + k]; b += a; } a %= 65521u; b %= 65521u; i += n; }
+    std::vector<unsigned char> z; z.reserve(rawSize + rawSize / 65535 * 5 + 16);
+    z.push_back(0x78); z.push_back(0x01);                                                            // zlib header: deflate, 32 K window, no preset
+    for (size_t i = 0; i < rawSize;) {
+        const size_t n = std::min<size_t>(65535, rawSize - i);
+        z.push_back(i + n == rawSize ? 1 : 0);                                                       // BFINAL, BTYPE = 00 (stored)
+        z.push_back(n & 0xFF); z.push_back((n >> 8) & 0xFF); z.push_back(~n & 0xFF); z.push_back((~n >> 8) & 0xFF);
+        z.insert(z.end(), raw.begin() + i, raw.begin() + i + n);
+        i += n;
+    }
+    put_be32(z, (b << 16) | a);
+    ok = ok && write_chunk(fp, "IDAT", z) && write_chunk(fp, "IEND", std::vector<unsigned char>());
+    return (fclose(fp) == 0) && ok;
+}
+
 // ---- image function: image.cpp:285-346 (generateImageFunction) -------------------------------------------------------
 static bool generateImageFunction(const float* rgbPixels, unsigned int imageWidth, unsigned int imageHeight,
                                   std::vector<float>& result, unsigned int& outW, unsigned int& outH)

@@ -298,24 +298,26 @@ void Renderer::saveImage(const std::string& file)                               
 {
     if (!m_initialized) return;
     const int xres = m_renderSettings.m_imageResolution.x, yres = m_renderSettings.m_imageResolution.y;
+    const std::string ext = file.size() > 4 ? file.substr(file.size() - 4) : std::string();
+    if (ext == ".png" || ext == ".ppm") {
+        // 8-bit formats: conversion + vertical flip (the reference's negative stride, :1131-1136) on the device, 4 B/pixel read back
+        std::vector<unsigned char> px((size_t)xres * yres * 4);
+        if (vt_read_display(m_ctx, &px[0], 1) != VT_OK) { m_status = vt_last_error(m_ctx); return; }
+        if (ext == ".png") { if (!writePNG(file, &px[0], xres, yres)) log("could not write " + file); return; }
+        FILE* fp = fopen(file.c_str(), "wb");
+        if (!fp) return;
+        fprintf(fp, "P6\n%d %d\n255\n", xres, yres);
+        for (size_t i = 0; i < (size_t)xres * yres; ++i) fwrite(&px[4 * i], 1, 3, fp);
+        fclose(fp);
+        return;
+    }
     std::vector<float> pixels((size_t)xres * yres * 4);
     if (!readAverage(&pixels[0])) return;
-    const bool ppm = file.size() > 4 && file.substr(file.size() - 4) == ".ppm";
     FILE* fp = fopen(file.c_str(), "wb");
     if (!fp) return;
-    if (ppm) {
-        fprintf(fp, "P6\n%d %d\n255\n", xres, yres);
-        for (int y = yres - 1; y >= 0; --y)                                        // vertical flip: GL row 0 is the bottom row
-            for (int x = 0; x < xres; ++x)
-                for (int c = 0; c < 3; ++c) {
-                    const float v = pixels[((size_t)y * xres + x) * 4 + c];
-                    fputc((int)(std::min(1.0f, std::max(0.0f, v == v ? v : 0.0f)) * 255.0f + 0.5f), fp);
-                }
-    } else {
-        fprintf(fp, "PF\n%d %d\n-1.0\n", xres, yres);                              // PFM stores bottom-to-top = GL order
-        for (int y = 0; y < yres; ++y)
-            for (int x = 0; x < xres; ++x) fwrite(&pixels[((size_t)y * xres + x) * 4], sizeof(float), 3, fp);
-    }
+    fprintf(fp, "PF\n%d %d\n-1.0\n", xres, yres);                              // PFM stores bottom-to-top = GL order
+    for (int y = 0; y < yres; ++y)
+        for (int x = 0; x < xres; ++x) fwrite(&pixels[((size_t)y * xres + x) * 4], sizeof(float), 3, fp);
     fclose(fp);
 }
 

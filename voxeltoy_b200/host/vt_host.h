@@ -255,6 +255,7 @@ bool calculateCDF(const float* rgbPixels, unsigned int imageWidth, unsigned int 
                   std::vector<float>& cdfUData, unsigned int& cdfUDataWidth, unsigned int& cdfUDataHeight,
                   std::vector<float>& cdfVData, float& environmentTextureIntegral);
 bool writePFM(const std::string& path, const float* rgb, unsigned int w, unsigned int h);
+bool writePNG(const std::string& path, const unsigned char* rgba8, unsigned int w, unsigned int h);   // rows top-down, stored deflate
 
 // ---- renderer/services/service.h:13-77 ------------------------------------------------------------------------------
 class Renderer;
@@ -312,7 +313,7 @@ public:
     void setVoxelData(const vtm::V3i& resolution, const std::vector<int32_t>& voxelMaterials, const std::vector<float>& materialData,
                       const std::vector<int32_t>& emissiveVoxelIndices);
     void pruneInteriorEmissiveVoxels(const std::vector<int32_t>& voxelMaterials, vtm::V3i& volumeResolution, std::vector<int32_t>& emissiveVoxelIndices);
-    void saveImage(const std::string& file);                   // writes .pfm (float) or .ppm (8 bit), vertically flipped like the reference
+    void saveImage(const std::string& file);                   // .pfm (float RGB) or .png / .ppm (8 bit, vt_read_display), vertically flipped like the reference
     bool readAverage(float* rgbaOut);                          // GL orientation (row 0 = bottom)
     void resetRender();
     bool onMouseMove(int dx, int dy, int buttons);
