@@ -65,6 +65,10 @@ _SIG = {
     "vth_cdf_dims": (None, [P, C.POINTER(C.c_uint), C.POINTER(C.c_uint), f32p]),
     "vth_cdf_copy": (None, [P, f32p, f32p]), "vth_cdf_free": (None, [P]),
     "vth_write_pfm": (C.c_int, [C.c_char_p, f32p, C.c_uint, C.c_uint]),
+    "vth_renderer_resolution": (None, [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vth_widget_create": (P, [P]), "vth_widget_destroy": (None, [P]),
+    "vth_widget_run_script": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_int]), "vth_widget_pump": (C.c_int, [P, C.c_int]),
+    "vth_widget_update_pending": (C.c_int, [P]), "vth_widget_paints": (C.c_ulong, [P]),
     "vth_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint, C.c_uint]),
     "vth_load_image_dims": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "vth_load_image": (C.c_int, [C.c_char_p, f32p]),
@@ -348,6 +352,11 @@ class Renderer:
         self._L.vth_renderer_update_material_value(self._h, offset, float(v))
 
     # new-build accessors
+    def renderSettingsResolution(self):
+        w = C.c_int(); h = C.c_int()
+        self._L.vth_renderer_resolution(self._h, C.byref(w), C.byref(h))
+        return w.value, h.value
+
     def numberSamples(self):
         return self._L.vth_renderer_number_samples(self._h)
 
@@ -392,6 +401,36 @@ class Tool:
     def __del__(self):
         try:
             self._L.vth_tool_destroy(self._h)
+        except Exception:
+            pass
+
+
+class HeadlessWidget:
+    """The reference's GLWidget (ui/glwidget.cpp) without Qt: event routing tool -> renderer, UI slots, repaint while samples
+    are pending. `run(script)` plays one command per line (host/headless.cpp lists them)."""
+
+    def __init__(self, renderer):
+        self._L = lib(); self._r = renderer; self._h = self._L.vth_widget_create(renderer._h)
+
+    def run(self, script):
+        err = C.create_string_buffer(512)
+        if self._L.vth_widget_run_script(self._h, script.encode(), err, 512) != 0:
+            raise ValueError(err.value.decode())
+        res = self._r.renderSettingsResolution()
+        self._r.width, self._r.height = res
+
+    def pump(self, max_paints=1000000):
+        return self._L.vth_widget_pump(self._h, int(max_paints))
+
+    def updatePending(self):
+        return bool(self._L.vth_widget_update_pending(self._h))
+
+    def paints(self):
+        return int(self._L.vth_widget_paints(self._h))
+
+    def __del__(self):
+        try:
+            self._L.vth_widget_destroy(self._h)
         except Exception:
             pass
 

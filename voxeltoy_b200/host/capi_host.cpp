@@ -115,6 +115,22 @@ int vth_tool_mouse(void* t, int press, int x, int y, int buttons, int modifiers,
     return (press ? tool->mousePressEvent(&e, s) : tool->mouseMoveEvent(&e, s)) ? 1 : 0;
 }
 
+// ---- headless widget (ui/glwidget.cpp without Qt) ----------------------------------------------------------------------
+void* vth_widget_create(void* renderer) { return new HeadlessWidget(R(renderer)); }
+void vth_widget_destroy(void* w) { delete static_cast<HeadlessWidget*>(w); }
+int vth_widget_run_script(void* w, const char* script, char* error, int errorSize)
+{
+    std::string err;
+    const bool ok = static_cast<HeadlessWidget*>(w)->runScript(script ? script : "", err);
+    if (error && errorSize > 0) { strncpy(error, err.c_str(), (size_t)errorSize - 1); error[errorSize - 1] = 0; }
+    return ok ? 0 : -1;
+}
+int vth_widget_pump(void* w, int maxPaints) { return static_cast<HeadlessWidget*>(w)->pump(maxPaints); }
+int vth_widget_update_pending(void* w) { return static_cast<HeadlessWidget*>(w)->updatePending() ? 1 : 0; }
+unsigned long vth_widget_paints(void* w) { return static_cast<HeadlessWidget*>(w)->paints(); }
+void vth_renderer_resolution(void* r, int* w, int* h) { *w = R(r).renderSettings().m_imageResolution.x; *h = R(r).renderSettings().m_imageResolution.y; }
+void vth_widget_size(void* w, int* width, int* height) { *width = static_cast<HeadlessWidget*>(w)->width(); *height = static_cast<HeadlessWidget*>(w)->height(); }
+
 // ---- loaders -------------------------------------------------------------------------------------------------------------
 void* vth_vox_load(const char* path)
 {

@@ -392,3 +392,65 @@ public:
 private:
     Renderer& m_renderer;
 };
+
+// ---- ui/glwidget.h: the widget that drives the renderer, without Qt ----------------------------------
+// Same members, slots and event routing as GLWidget (ui/glwidget.cpp:22-410); Qt's update() -> paintGL() round trip is an
+// explicit flag that pump() drains, so a script (runScript) or a server loop can play real event traffic against Renderer.
+class HeadlessWidget {
+public:
+    enum ResolutionMode { RM_FIXED, RM_LONGEST_AXIS, RM_MATCH_WINDOW };          // ui/renderpropertiesui.h
+    enum ToolAction { ACTION_SELECT_FOCAL_POINT, ACTION_EDIT_VOXELS };            // ui/mainwindow.h
+    explicit HeadlessWidget(Renderer& renderer);
+    ~HeadlessWidget();
+    // QGLWidget side
+    void resizeGL(int width, int height);
+    bool paintGL();                                   // true when another repaint was scheduled (samples pending)
+    int pump(int maxPaints);                          // runs paintGL while an update is pending; returns the number of paints
+    void mousePressEvent(const MouseEvent& e);
+    void mouseMoveEvent(const MouseEvent& e);
+    void mouseReleaseEvent(const MouseEvent& e);
+    void keyPressEvent(const KeyEvent& e);
+    // slots (glwidget.cpp:225-410)
+    void cameraFStopChanged(float fstop);
+    void cameraFocalLengthChanged(float length);
+    void cameraLensModelChanged(int model);
+    void cameraControllerChanged(const std::string& mode);
+    void onPathtracerMaxSamplesChanged(int value);
+    void onPathtracerMaxPathBouncesChanged(int value);
+    void onWireframeOpacityChanged(int value);
+    void onWireframeThicknessChanged(int value);
+    void loadMesh(const std::string& file);
+    size_t loadVoxFile(const std::string& file);      // returns the number of materials announced (materialCreated signals)
+    void saveImage(const std::string& file);
+    void onResolutionSettingsChanged(ResolutionMode mode, int axis1, int axis2);
+    void onActionTriggered(int action, bool triggered);
+    void onBackgroundColorChangedConstant(const vtm::V3f& color);
+    void onBackgroundColorChangedGradientFrom(const vtm::V3f& color);
+    void onBackgroundColorChangedGradientTo(const vtm::V3f& color);
+    void onBackgroundColorChangedImage(const std::string& path);
+    void onBackgroundImageRotationChanged(int rotation);
+    void onBeginUserInteraction();
+    void onEndUserInteraction();
+    void onMaterialColorChanged(unsigned int dataOffset, const float rgb[3]);
+    void onMaterialValueChanged(unsigned int dataOffset, float value);
+    // script player: one command per line (see headless.cpp); returns false and fills `error` at the first bad line
+    bool runScript(const std::string& script, std::string& error);
+    bool updatePending() const { return m_updatePending; }
+    int width() const { return m_width; }
+    int height() const { return m_height; }
+    unsigned long paints() const { return m_paints; }
+private:
+    void update() { m_updatePending = true; }
+    void resizeRender(int renderW, int renderH, int windowW, int windowH);
+    Renderer& m_renderer;
+    ResolutionMode m_resolutionMode;
+    int m_resolutionLongestAxis;
+    Tool* m_activeTool;
+    unsigned int m_activeUserDialogs;
+    int m_lastPos[2];
+    int m_lastMouseButtons;
+    int m_width, m_height;
+    bool m_updatePending;
+    unsigned long m_paints;
+};
+
