@@ -239,7 +239,8 @@ def main():
         r.renderPasses(PASSES)
         if world > 1:
             reduce_step()
-            pinned_out.copy_(reduce_buf, non_blocking=True)
+            if rank == 0:                                                  # the combined frame lives on rank 0 (reduce, dst=0)
+                pinned_out.copy_(reduce_buf, non_blocking=True)
             stream.synchronize()
         else:
             r.readAverage(pinned_out)
