@@ -3,8 +3,9 @@
 
 Metric (BASELINE.json): path-traced Msamples/s @1080p, 4 bounces. Workload at every N: BASELINE config 2,
 `resources/scene_fall.vox` at 1920x1080, 4 bounces, importance-sampled IBL + thin-lens DOF (synthetic HDR
-environment). One STEP = one batch of PASSES progressive passes over the whole frame through
-vt_render (path trace fused with the running accumulation). With N GPUs the samples are partitioned
+environment). One STEP = the whole job of that config: 256 progressive passes (256 spp) over the frame through
+Renderer::renderPasses -> vt_render, which runs them as batches of 16 passes (32 Mi paths in flight), path trace fused with
+the running accumulation (--passes changes the step size). With N GPUs the samples are partitioned
 (rank r renders sampleCount = p*N + r): per-GPU work is fixed (weak scaling) and each step ends
 with an NCCL reduce of the float4 accumulators to rank 0 inside the timed region.
 
@@ -24,9 +25,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, BOUNCES, PASSES = 1920, 1080, 4, 8
+W, H, BOUNCES, PASSES = 1920, 1080, 4, 256
 THETA, PHI, FSTOP = 120.0, 30.0, 2.8
-WORKLOAD = "C2: scene_fall.vox 1920x1080, 4 bounces, IBL + thin-lens DOF, %d passes/step" % PASSES
+WORKLOAD_FMT = "C2: scene_fall.vox 1920x1080, 4 bounces, IBL + thin-lens DOF, %d spp per step (batches of <= 32 Mi paths = 16 passes)"
+WORKLOAD = WORKLOAD_FMT % PASSES
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -129,13 +131,16 @@ def cpu_reference_run(steps, warmup, sample_rows=None):
 
 
 def main():
+    global PASSES, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--passes", type=int, default=PASSES, help="progressive passes (spp) per step; BASELINE config 2 is 256")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    PASSES = max(1, args.passes); WORKLOAD = WORKLOAD_FMT % PASSES
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(3, args.warmup)
