@@ -224,3 +224,67 @@ def test_full_size_properties_c3_c4(vt_ctx):
     mega = vt_ctx.read_average()
     vt_ctx.set_kernel_variant(2)
     assert util.same_bits(mega, full).all()
+
+
+def _dense_noise_offsets_torch(n, offsets, density=0.35, seed=1, n_materials=8, chunk=64):
+    """scenes.dense_noise_grid + ids_to_offsets with torch on the GPU (test plumbing: the numpy generator needs 40 s at 1024^3);
+    same integers, checked against the numpy version below."""
+    import torch
+    dev = torch.device("cuda:0")
+    M = 0xFFFFFFFF
+    out = torch.empty((n, n, n), dtype=torch.int32)
+    x = torch.arange(n, dtype=torch.int64, device=dev)[None, None, :]
+    y = torch.arange(n, dtype=torch.int64, device=dev)[None, :, None]
+    offs = torch.as_tensor(np.asarray(offsets, np.int64), device=dev)
+    thr = int(density * 2 ** 32)
+    for z0 in range(0, n, chunk):
+        z = torch.arange(z0, min(n, z0 + chunk), dtype=torch.int64, device=dev)[:, None, None]
+        v = (x + y * n + z * (n * n) + seed * 0x9E3779B9) & M
+        v = (v * 747796405 + 2891336453) & M                                   # scenes.pcg_hash
+        w = ((torch.bitwise_right_shift(v, (v >> 28) + 4) ^ v) * 277803737) & M
+        h = ((w >> 22) ^ w) & M
+        ids = (h >> 8) & (n_materials - 1)
+        out[z0:z0 + chunk] = torch.where(h < thr, offs[ids], torch.full_like(ids, -1)).to(torch.int32).cpu()
+    return out.reshape(-1).numpy()
+
+
+def test_full_size_properties_c5(vt_ctx):
+    """BASELINE config 5 at FULL size (dense noise 1024^3, 35 % solid, 3840x2160, 16 bounces) through size-independent properties:
+    the wavefront renderer equals the megakernel bit for bit, rank r of a sample partition renders exactly sample index p*N + r,
+    and the scripted pick -> add edit puts a voxel where the picked face points, after which a pick at the same pixel finds it."""
+    t = scenes.MaterialTable()
+    for k in range(8):
+        (t.metal((0.9, 0.6 + 0.04 * k, 0.3), 30.0 + 20 * k) if k % 3 == 2 else t.lambert((0.3 + 0.08 * k, 0.5, 0.9 - 0.08 * k)))
+    small = scenes.ids_to_offsets(scenes.dense_noise_grid(32, density=0.35), t.offsets)
+    assert np.array_equal(_dense_noise_offsets_torch(32, t.offsets), small)    # the torch generator is the numpy one
+    n = 1024
+    grid = _dense_noise_offsets_torch(n, t.offsets)
+    solid = int((grid[: n * n * 8] >= 0).sum())
+    assert abs(solid / float(n * n * 8) - 0.35) < 0.002
+    d = util.make_frame(dict(res=(n, n, n), grid=grid, materials=t.array(), emissive=np.zeros(0, np.int32)), 3840, 2160, bounces=16,
+                        theta=125, phi=40)
+    util.upload(vt_ctx, d)
+    del grid
+    vt_ctx.render(0, 1)
+    s0 = vt_ctx.read_average()
+    vt_ctx.set_kernel_variant(0); vt_ctx.reset_accumulation(); vt_ctx.render(0, 1)
+    assert util.same_bits(vt_ctx.read_average(), s0).all()
+    vt_ctx.set_kernel_variant(2)
+    vt_ctx.reset_accumulation(); vt_ctx.render(3, 1)                           # sample index 3 on its own
+    s3 = vt_ctx.read_average()
+    vt_ctx.set_partition(vt.VT_PART_SAMPLES, 1, 2)                             # rank 1 of 2: pass p renders sample 2p + 1
+    vt_ctx.reset_accumulation(); vt_ctx.render(1, 1)                           # its pass 1 -> sample 3 (the accumulator keeps the SUM)
+    assert util.same_bits(vt_ctx.read_average(), s3).all()
+    vt_ctx.set_partition(vt.VT_PART_NONE, 0, 1)
+    # edit: pick at the image centre, add on the picked face, pick again
+    vt_ctx.pick(1920.0, 1080.0)
+    sel, normal = vt_ctx.get_selection()
+    assert np.abs(normal[:3]).sum() == 1.0                                     # a face of a voxel was hit
+    vt_ctx.add_voxel(0.0, 0.0)
+    vt_ctx.pick(1920.0, 1080.0)
+    sel2, _ = vt_ctx.get_selection()
+    assert np.array_equal(sel2[:3], sel[:3] + normal[:3].astype(np.int32))
+    vt_ctx.remove_voxel()
+    vt_ctx.pick(1920.0, 1080.0)
+    assert np.array_equal(vt_ctx.get_selection()[0][:3], sel[:3])
+    vt_ctx.volume_upload(np.full(16 ** 3, -1, np.int32), (16, 16, 16))         # release the 4 GiB grid
