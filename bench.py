@@ -4,7 +4,7 @@
 Metric (BASELINE.json): path-traced Msamples/s @1080p, 4 bounces. Workload at every N: BASELINE config 2,
 `resources/scene_fall.vox` at 1920x1080, 4 bounces, importance-sampled IBL + thin-lens DOF (synthetic HDR
 environment). One STEP = the whole job of that config: 256 progressive passes (256 spp) over the frame through
-Renderer::renderPasses -> vt_render, which runs them as batches of 16 passes (32 Mi paths in flight), path trace fused with
+Renderer::renderPasses -> vt_render, which runs them as batches of 64 passes (128 Mi paths in flight), path trace fused with
 the running accumulation (--passes changes the step size). With N GPUs the samples are partitioned
 (rank r renders sampleCount = p*N + r): per-GPU work is fixed (weak scaling) and each step ends
 with an NCCL reduce of the float4 accumulators to rank 0 inside the timed region.
@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 W, H, BOUNCES, PASSES = 1920, 1080, 4, 256
 THETA, PHI, FSTOP = 120.0, 30.0, 2.8
-WORKLOAD_FMT = "C2: scene_fall.vox 1920x1080, 4 bounces, IBL + thin-lens DOF, %d spp per step (batches of <= 32 Mi paths = 16 passes)"
+WORKLOAD_FMT = "C2: scene_fall.vox 1920x1080, 4 bounces, IBL + thin-lens DOF, %d spp per step (batches of <= 128 Mi paths = 64 passes)"
 WORKLOAD = WORKLOAD_FMT % PASSES
 
 

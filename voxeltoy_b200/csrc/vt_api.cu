@@ -73,7 +73,7 @@ struct vt_ctx {
     WfCounts* d_wf_counts[kWfLanes] = {nullptr, nullptr, nullptr, nullptr}; int wf_counts_cap[kWfLanes] = {0, 0, 0, 0};
     cudaStream_t wf_stream[kWfLanes] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t wf_fork = nullptr, wf_done[kWfLanes] = {nullptr, nullptr, nullptr, nullptr}, wf_acc[kWfLanes] = {nullptr, nullptr, nullptr, nullptr};
-    size_t wf_max_paths = (size_t)32 << 20;
+    size_t wf_max_paths = (size_t)128 << 20;   // paths in flight per batch: 340 B each -> <= 45.6 GB of the 180 GB (C2: 32 -> 64 -> 128 Mi = 2 542 -> 2 582 -> 2 607 Msamples/s)
     int wf_shade_blocks[2] = {0, 0}, wf_trace_blocks[2] = {0, 0}, wf_sms = 0;
     // per-kernel device timing (vt_kernel_timing_enable): event pairs around every wavefront launch
     bool timing = false;
