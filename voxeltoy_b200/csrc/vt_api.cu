@@ -772,7 +772,7 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
     const int ci = COUNT ? 1 : 0;
     if (c->wf_shade_blocks[ci] == 0) {
         int per_sm_s = 0, per_sm_t = 0, sms = 0;
-        VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, wf_shade_kernel<COUNT>, 128, 0));
+        VT_CUDA(c, wf_shade_blocks_per_sm(COUNT, &per_sm_s));
         VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, wf_trace_kernel<COUNT, true>, 256, 0));
         VT_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
         if (const char* e = getenv("VT_WF_SHADE_CTAS")) { const int v = atoi(e); if (v >= 1) per_sm_s = std::min(per_sm_s, v); }   // tuning knobs
@@ -814,7 +814,7 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
             { WfTimer t(c, VT_K_TRACE, st); if (V.dist != nullptr && !COUNT) wf_trace_kernel<COUNT, true><<<c->wf_trace_blocks[ci], 256, 0, st>>>(V, S, cur, cn + it, c->d_counters);
               else wf_trace_kernel<COUNT, false><<<c->wf_trace_blocks[ci], 256, 0, st>>>(V, S, cur, cn + it, c->d_counters); }
             { WfTimer t(c, VT_K_CLASSIFY, st); wf_classify_kernel<<<classify_blocks, 256, 0, st>>>(V, F, L, S, cur, pass0, cn + it, cn + it + 1, it == 0 ? prim : nullptr); }
-            { WfTimer t(c, VT_K_SHADE, st); wf_shade_kernel<COUNT><<<c->wf_shade_blocks[ci], 128, 0, st>>>(V, F, S, cur, nxt, cn + it + 1, c->d_counters); }
+            { WfTimer t(c, VT_K_SHADE, st); wf_shade_launch(COUNT, (unsigned)c->wf_shade_blocks[ci], st, V, F, S, cur, nxt, cn + it + 1, c->d_counters); }
             c->launches += 3;
             if (it == F.max_bounces) break;
         }

@@ -10,16 +10,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef VT_GLOBAL
+#define VT_GLOBAL static __global__
+#endif
 #define VT_ENV_MAX_CDF_SIZE 512          // image.cpp:14
 
-__global__ void vt_env_rgba_kernel(const float* __restrict__ rgb, float4* __restrict__ out, size_t n)
+VT_GLOBAL void vt_env_rgba_kernel(const float* __restrict__ rgb, float4* __restrict__ out, size_t n)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;        // renderer.cpp:994-1002: GL_RGB -> GL_RGBA32F, alpha 1
     if (i < n) out[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 1.0f);
 }
 
 // image.cpp:309-335: box filter by integer factors (double accumulator, rows then columns), Rec.709 luminance
-__global__ void vt_env_luminance_kernel(const float* __restrict__ rgb, int w, int nw, int nh, int fx, int fy, float* __restrict__ lum)
+VT_GLOBAL void vt_env_luminance_kernel(const float* __restrict__ rgb, int w, int nw, int nh, int fx, int fy, float* __restrict__ lum)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= nw || y >= nh) return;
@@ -35,7 +38,7 @@ __global__ void vt_env_luminance_kernel(const float* __restrict__ rgb, int w, in
 }
 
 // image.cpp:337-342: one axis of the separable 3x3 gaussian (1/4, 1/2, 1/4), edges clamped
-__global__ void vt_env_blur_kernel(const float* __restrict__ in, float* __restrict__ out, int w, int h, int vertical)
+VT_GLOBAL void vt_env_blur_kernel(const float* __restrict__ in, float* __restrict__ out, int w, int h, int vertical)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w || y >= h) return;
@@ -50,7 +53,7 @@ __global__ void vt_env_blur_kernel(const float* __restrict__ in, float* __restri
 
 // image.cpp:361-375: functionU = max(0, value) * sinTheta(row); the sine table comes from the host (double-precision
 // libm sin of M_PI * (y + 0.5f) / H, rounded to float: the device's double sin is not bit-compatible with glibc's)
-__global__ void vt_env_function_kernel(const float* __restrict__ img, const float* __restrict__ sin_row, int w, int h, float* __restrict__ fu)
+VT_GLOBAL void vt_env_function_kernel(const float* __restrict__ img, const float* __restrict__ sin_row, int w, int h, float* __restrict__ fu)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w || y >= h) return;
@@ -60,7 +63,7 @@ __global__ void vt_env_function_kernel(const float* __restrict__ img, const floa
 
 // image.cpp:372: textureTimesSinSum += value * sinTheta, row-major, one chain of rounded float additions.
 // One CTA: all threads stage a tile in shared memory, thread 0 folds it in order.
-__global__ void __launch_bounds__(256) vt_env_sum_kernel(const float* __restrict__ fu, size_t n, float* __restrict__ out)
+VT_GLOBAL void __launch_bounds__(256) vt_env_sum_kernel(const float* __restrict__ fu, size_t n, float* __restrict__ out)
 {
     constexpr int kTile = 4096;
     __shared__ float tile[kTile];
@@ -102,7 +105,7 @@ __device__ __forceinline__ float env_scan_warp(const float* __restrict__ f, int 
     return total;
 }
 
-__global__ void __launch_bounds__(128) vt_env_cdf_rows_kernel(const float* __restrict__ fu, int w, int h, float* __restrict__ cdf_u, float* __restrict__ fv)
+VT_GLOBAL void __launch_bounds__(128) vt_env_cdf_rows_kernel(const float* __restrict__ fu, int w, int h, float* __restrict__ cdf_u, float* __restrict__ fv)
 {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= h) return;
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(128) vt_env_cdf_rows_kernel(const float* __res
     if ((threadIdx.x & 31) == 0) fv[row] = total;
 }
 
-__global__ void __launch_bounds__(32) vt_env_cdf_v_kernel(const float* __restrict__ fv, int h, float* __restrict__ cdf_v)
+VT_GLOBAL void __launch_bounds__(32) vt_env_cdf_v_kernel(const float* __restrict__ fv, int h, float* __restrict__ cdf_v)
 {
     env_scan_warp(fv, h, (float)(unsigned int)h, cdf_v);
 }
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(32) vt_env_cdf_v_kernel(const float* __restric
 // Guide tables (vt_api.cu build_guide / vt_device.cuh cdf_search_guided): for CDF row r (n entries, `stride` apart)
 // guide[j] = max({0} U {m in [1, n-2] : cdf[m] <= j/K}), guide[K] = n-2; *sorted is cleared when some row's
 // cdf[1..n-2] is not non-decreasing (then the device keeps the literal bisection of envMapSample.h:70-123).
-__global__ void vt_env_guide_kernel(const float* __restrict__ cdf, int n, int stride, int rows, int K, unsigned short* __restrict__ guide, int* __restrict__ sorted)
+VT_GLOBAL void vt_env_guide_kernel(const float* __restrict__ cdf, int n, int stride, int rows, int K, unsigned short* __restrict__ guide, int* __restrict__ sorted)
 {
     const int r = blockIdx.x;
     if (r >= rows) return;

@@ -27,7 +27,7 @@ struct RenderLaunch {
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128, 4)
+VT_GLOBAL void __launch_bounds__(128, 4)
 vt_render_kernel(const Volume V, const Frame F, const RenderLaunch L,
                  float4* __restrict__ accum, int* __restrict__ primary, Counters* __restrict__ counters)
 {
@@ -82,7 +82,7 @@ vt_render_kernel(const Volume V, const Frame F, const RenderLaunch L,
 
 // ---- services ------------------------------------------------------------------------------
 // selectVoxel.vs:36-71. The pick ray is the un-jittered pinhole ray.
-__global__ void vt_pick_kernel(const Volume V, const Frame F, float px, float py, Shared* sh)
+VT_GLOBAL void vt_pick_kernel(const Volume V, const Frame F, float px, float py, Shared* sh)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Tally<false> tl; tl.clear();
@@ -100,7 +100,7 @@ __global__ void vt_pick_kernel(const Volume V, const Frame F, float px, float py
 }
 
 // focalDistance.vs:45-81
-__global__ void vt_pick_focal_kernel(const Volume V, const Frame F, float px, float py, Shared* sh)
+VT_GLOBAL void vt_pick_focal_kernel(const Volume V, const Frame F, float px, float py, Shared* sh)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Tally<false> tl; tl.clear();
@@ -125,7 +125,7 @@ VT_DEV void set_voxel_bits(unsigned long long* bricks, const Volume& V, int x, i
 }
 
 // addVoxel.vs:16-41. result[0] = 1 if a voxel was written, result[1..3] = its coordinate.
-__global__ void vt_add_voxel_kernel(const Volume V, const Frame F, float mx, float my, const Shared* sh,
+VT_GLOBAL void vt_add_voxel_kernel(const Volume V, const Frame F, float mx, float my, const Shared* sh,
                                     int* mat, unsigned long long* bricks, int* result)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -162,7 +162,7 @@ __global__ void vt_add_voxel_kernel(const Volume V, const Frame F, float mx, flo
 }
 
 // removeVoxel.vs:8-11 (contract N2: the voxel becomes empty)
-__global__ void vt_remove_voxel_kernel(const Volume V, const Shared* sh,
+VT_GLOBAL void vt_remove_voxel_kernel(const Volume V, const Shared* sh,
                                        int* mat, unsigned long long* bricks, int* result)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -177,7 +177,7 @@ __global__ void vt_remove_voxel_kernel(const Volume V, const Shared* sh,
 // ---- occupancy layout ------------------------------------------------------------------------
 // one thread per (brick, z-slice-of-4): builds 16 bits; a 4-thread group ORs them with shuffles.
 // Simpler and fast enough (upload-time only): one thread per brick row (4 voxels in x) -> atomicOr.
-__global__ void vt_build_bricks_kernel(const int* __restrict__ mat, unsigned long long* __restrict__ bricks,
+VT_GLOBAL void vt_build_bricks_kernel(const int* __restrict__ mat, unsigned long long* __restrict__ bricks,
                                        int X, int Y, int Z, int BX, int PBX, int BXY)
 {
     // thread -> (bx, y, z): reads up to 4 consecutive ints
@@ -202,7 +202,7 @@ __global__ void vt_build_bricks_kernel(const int* __restrict__ mat, unsigned lon
 // sentinel shell: sets the bit of every voxel of the PADDED brick array that lies outside the volume (one thread per brick).
 // A DDA that leaves the volume lands on such a voxel in its very next iteration (a step changes each coordinate by at most 1),
 // so the stepping loop needs no bounds test of its own (dda_step).
-__global__ void vt_sentinel_kernel(unsigned long long* __restrict__ padded, int X, int Y, int Z, int PBX, int PBY, int PBZ)
+VT_GLOBAL void vt_sentinel_kernel(unsigned long long* __restrict__ padded, int X, int Y, int Z, int PBX, int PBY, int PBZ)
 {
     const size_t n = (size_t)PBX * PBY * PBZ;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -221,7 +221,7 @@ __global__ void vt_sentinel_kernel(unsigned long long* __restrict__ padded, int 
 
 // ---- empty-space distance field (Volume::dist, dda_skip) ----------------------------------------------------------
 // pass 0: one thread per 8^3 cell: 0 if any in-volume voxel of its 2x2x2 bricks is set, else `cap`
-__global__ void vt_dist_init_kernel(const unsigned long long* __restrict__ bricks, unsigned char* __restrict__ dist,
+VT_GLOBAL void vt_dist_init_kernel(const unsigned long long* __restrict__ bricks, unsigned char* __restrict__ dist,
                                     int X, int Y, int Z, int PBX, int BXY, int CX, int CY, int CZ, int cap)
 {
     const int n = CX * CY * CZ;
@@ -243,7 +243,7 @@ __global__ void vt_dist_init_kernel(const unsigned long long* __restrict__ brick
 // Chebyshev distance transform, separable: d(c) = min over (jx, jy, jz) of max(|jx|, |jy|, |jz|) with solid(c + j)
 //   = min_jz max(|jz|, min_jy max(|jy|, min_jx max(|jx|, [0 if solid(c + j) else cap]))) -- one 1-D pass per axis.
 // axis: 0 x, 1 y, 2 z; values are capped at `cap`; cells outside the grid impose nothing.
-__global__ void vt_dist_pass_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int CX, int CY, int CZ, int axis, int cap)
+VT_GLOBAL void vt_dist_pass_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int CX, int CY, int CZ, int axis, int cap)
 {
     const int n = CX * CY * CZ;
     const int stride = (axis == 0) ? 1 : (axis == 1 ? CX : CX * CY);
@@ -261,7 +261,7 @@ __global__ void vt_dist_pass_kernel(const unsigned char* __restrict__ in, unsign
 }
 
 // material-offset grid from occupancy: voxel = bit ? fill : -1. One thread per x-run of 4 voxels.
-__global__ void vt_fill_offsets_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
+VT_GLOBAL void vt_fill_offsets_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
                                        int X, int Y, int Z, int BX, int PBX, int BXY, int fill)
 {
     const size_t n = (size_t)BX * (size_t)Y * (size_t)Z;
@@ -284,7 +284,7 @@ __global__ void vt_fill_offsets_kernel(const unsigned long long* __restrict__ br
 }
 
 // lazy counterpart of vt_fill_solid_kernel: writes -1 into every voxel whose occupancy bit is clear (one thread per x-run of 4)
-__global__ void vt_clear_empty_offsets_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
+VT_GLOBAL void vt_clear_empty_offsets_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
                                               int X, int Y, int Z, int BX, int PBX, int BXY)
 {
     const size_t n = (size_t)BX * (size_t)Y * (size_t)Z;
@@ -301,7 +301,7 @@ __global__ void vt_clear_empty_offsets_kernel(const unsigned long long* __restri
 
 // sparse variant used by vt_voxelize: the grid was cleared to -1 by a memset; one thread per brick patches `fill` into the
 // voxels whose bit is set (in-volume bits only: boundary bricks also carry sentinel bits)
-__global__ void vt_fill_solid_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
+VT_GLOBAL void vt_fill_solid_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
                                      int X, int Y, int Z, int BX, int BY, int BZ, int PBX, int BXY, int fill)
 {
     const size_t n = (size_t)BX * BY * BZ;
@@ -329,7 +329,7 @@ VT_DEV float edge_d(f2 n, float va, float vb)                      // voxelize.g
     return dot(n, mk2(0.5f - va, 0.5f - vb)) + 0.5f * gmax(gabs(n.x), gabs(n.y));
 }
 
-__global__ void __launch_bounds__(128)
+VT_GLOBAL void __launch_bounds__(128)
 vt_voxelize_kernel(const float* __restrict__ xyz_in, const unsigned int* __restrict__ idx, int n_tris,
                    const float* __restrict__ M, int X, int Y, int Z, int BX, int BXY,
                    unsigned long long* __restrict__ bricks)
@@ -412,7 +412,7 @@ vt_voxelize_kernel(const float* __restrict__ xyz_in, const unsigned int* __restr
 
 // rule-based material assignment for solid voxels (BASELINE config 3):
 // rule 1: id = ((x>>5) ^ (y>>5) ^ (z>>5)) % n_table
-__global__ void vt_assign_materials_kernel(int* __restrict__ mat, int X, int Y, int Z,
+VT_GLOBAL void vt_assign_materials_kernel(int* __restrict__ mat, int X, int Y, int Z,
                                            const int* __restrict__ table, int n_table, int rule)
 {
     const size_t n = (size_t)X * Y * Z;
@@ -428,7 +428,7 @@ __global__ void vt_assign_materials_kernel(int* __restrict__ mat, int X, int Y, 
 // measurement hook: L2 read bandwidth (the north star quotes the path tracer against the L2 roofline, and the driver's
 // MEASURED_PEAKS.json only has HBM). Every thread streams 16-byte loads (ld.global.cg: cached in L2, not L1) over a buffer
 // that fits in L2, `reps` times.
-__global__ void __launch_bounds__(256)
+VT_GLOBAL void __launch_bounds__(256)
 vt_l2_read_kernel(const uint4* __restrict__ buf, size_t n_vec, int reps, unsigned int* __restrict__ sink)
 {
     unsigned int acc = 0;
@@ -443,7 +443,7 @@ vt_l2_read_kernel(const uint4* __restrict__ buf, size_t n_vec, int reps, unsigne
 }
 
 // test hook: advance_until on explicit operands, next to the literal loop it replaces
-__global__ void vt_advance_kernel(const float* __restrict__ d, const float* __restrict__ e, const float* __restrict__ tau,
+VT_GLOBAL void vt_advance_kernel(const float* __restrict__ d, const float* __restrict__ e, const float* __restrict__ tau,
                                   const int* __restrict__ nmax, size_t n, float* __restrict__ d_out, int* __restrict__ k_out, int literal)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -455,7 +455,7 @@ __global__ void vt_advance_kernel(const float* __restrict__ d, const float* __re
 }
 
 // test hook: the DDA alone
-__global__ void vt_trace_rays_kernel(const Volume V, const float* __restrict__ rays, size_t n, float* __restrict__ out)
+VT_GLOBAL void vt_trace_rays_kernel(const Volume V, const float* __restrict__ rays, size_t n, float* __restrict__ out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -472,7 +472,7 @@ __global__ void vt_trace_rays_kernel(const Volume V, const float* __restrict__ r
 // 8-bit UNORM as GL does it on a framebuffer write: clamp to [0, 1] (NaN -> 0), * 255, round to nearest even.
 __device__ __forceinline__ unsigned char unorm8(float v) { return (unsigned char)__float2int_rn(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f); }
 
-__global__ void vt_display_kernel(const float4* __restrict__ avg, uchar4* __restrict__ out, int W, int H, int flip)
+VT_GLOBAL void vt_display_kernel(const float4* __restrict__ avg, uchar4* __restrict__ out, int W, int H, int flip)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)W * H) return;

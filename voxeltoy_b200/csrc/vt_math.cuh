@@ -20,6 +20,16 @@
 #include <stdint.h>
 
 #define VT_DEV __device__ __forceinline__
+// kernels have internal linkage: the headers are compiled into more than one translation unit (vt_api.cu, vt_shade.cu)
+#define VT_GLOBAL static __global__
+// Division and pow are expanded at ~90 and ~20 sites of wf_shade (1 400 + 1 250 of its 6 700 instructions); that kernel
+// stalls on instruction fetch (14 % of its samples), so its translation unit (vt_shade.cu, VT_COMPACT_MATH) calls one
+// copy of each instead: shade -8 %. Everywhere else they stay inline (wf_generate is 6 % slower with calls).
+#ifdef VT_COMPACT_MATH
+#define VT_DEV_HEAVY static __device__ __noinline__
+#else
+#define VT_DEV_HEAVY __device__ __forceinline__
+#endif
 
 namespace vt {
 
@@ -37,7 +47,7 @@ VT_DEV f3 xyz(f4 v) { return mk3(v.x, v.y, v.z); }
 // IEEE binary32 division with the zero numerator peeled off. div.rn's inline fast path rejects a == 0 (FCHK) and calls a
 // ~60-instruction subroutine; axis-aligned normals, black albedo channels and zero throughput make that the common case
 // in shading (10 % of wf_shade's instructions before this). 0 / b = (sign a ^ sign b) 0 for every b except 0 and NaN.
-VT_DEV float gdiv(float a, float b)
+VT_DEV_HEAVY float gdiv(float a, float b)
 {
     if (a == 0.0f && b == b && b != 0.0f) return __int_as_float((__float_as_int(a) ^ __float_as_int(b)) & (int)0x80000000);
     return a / b;
@@ -152,7 +162,7 @@ VT_DEV float glog2(float x)
     return r;
 }
 
-VT_DEV float gpow(float x, float y) { return gexp2(y * glog2(x)); }
+VT_DEV_HEAVY float gpow(float x, float y) { return gexp2(y * glog2(x)); }
 
 VT_DEV int reduce_pio2(float x, float& r)
 {

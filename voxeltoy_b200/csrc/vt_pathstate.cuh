@@ -65,7 +65,7 @@ VT_DEV void begin_segment(const Volume& V, PathLane& p, int seg, f3 o, f3 d, int
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128)
+VT_GLOBAL void __launch_bounds__(128)
 vt_render_ps_kernel(const Volume V, const Frame F, const RenderLaunch L, int n_items,
                     float4* __restrict__ accum, int* __restrict__ primary, Counters* __restrict__ counters,
                     unsigned int* __restrict__ work_counter)

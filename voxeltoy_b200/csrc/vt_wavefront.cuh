@@ -221,7 +221,7 @@ VT_DEV void wf_flush_tally(const Tally<COUNT>& tl, Counters* __restrict__ counte
 // to the finish queue.
 // ---------------------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(256)
+VT_GLOBAL void __launch_bounds__(256)
 wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, const WfBuf out, int pass0,
                    WfCounts* __restrict__ cnt, int* __restrict__ primary, Counters* __restrict__ counters)
 {
@@ -279,7 +279,7 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
 #define VT_WF_TRACE_MIN_BLOCKS 6
 #endif
 template <bool COUNT, bool SKIP>
-__global__ void __launch_bounds__(256, VT_WF_TRACE_MIN_BLOCKS)
+VT_GLOBAL void __launch_bounds__(256, VT_WF_TRACE_MIN_BLOCKS)
 wf_trace_kernel(const Volume V, const WfState S, const WfBuf out, WfCounts* __restrict__ cnt, Counters* __restrict__ counters)
 {
     const unsigned full = 0xffffffffu;
@@ -374,7 +374,7 @@ wf_trace_kernel(const Volume V, const WfState S, const WfBuf out, WfCounts* __re
 // wf_classify: routes the paths of the generation just traced (pathTracer.fs:202-208, :214, :282-291).
 // Sequential over the generation's slots: coalesced reads, one shade-queue entry (the slot) per path.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+VT_GLOBAL void __launch_bounds__(256)
 wf_classify_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, const WfBuf out, int pass0,
                    const WfCounts* __restrict__ cin, WfCounts* __restrict__ cnext, int* __restrict__ primary)
 {
@@ -408,7 +408,7 @@ wf_classify_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
 // Queue 0 holds the paths that end here; queues 1..4 the surface hits sorted by material type.
 // ---------------------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(128, VT_WF_SHADE_MIN_BLOCKS)
+VT_GLOBAL void __launch_bounds__(128, VT_WF_SHADE_MIN_BLOCKS)
 wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, const WfBuf out, WfCounts* __restrict__ cnt,
                 Counters* __restrict__ counters)
 {
@@ -551,7 +551,7 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, 
 // ---------------------------------------------------------------------------------------------------------
 // wf_accumulate: accumulation.fs:10-18 over the batch's passes, in pass order. One thread per item.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+VT_GLOBAL void __launch_bounds__(256)
 wf_accumulate_kernel(const Frame F, const RenderLaunch L, const WfState S, int pass0, int n_batch, float4* __restrict__ accum)
 {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
@@ -571,5 +571,10 @@ wf_accumulate_kernel(const Frame F, const RenderLaunch L, const WfState S, int p
     }
     accum[pix] = avg;
 }
+
+// wf_shade_kernel is instantiated in its own translation unit (vt_shade.cu); these are its host-side entry points
+cudaError_t wf_shade_blocks_per_sm(bool count, int* blocks);
+void wf_shade_launch(bool count, unsigned int blocks, cudaStream_t st, const Volume& V, const Frame& F, const WfState& S, const WfBuf& in,
+                     const WfBuf& out, WfCounts* cnt, Counters* counters);
 
 } // namespace vt
