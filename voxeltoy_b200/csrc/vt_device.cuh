@@ -533,12 +533,15 @@ VT_DEV f3 background_color(const Frame& F, f3 v, Tally<COUNT>& tl)              
     const float bias = gmax(0.0f, v.y);
     return F.bg_bottom * (1.0f - bias) + F.bg_top * bias;
 }
+VT_DEV f4 env_with_pdf(const Frame& F, f3 L)                                         // lights.h:27-32, L = getBackgroundColor(wi)
+{
+    const float pdf = (F.use_image != 0) ? luminance(L) / F.env_integral : 1.0f / (4.0f * VT_PI);
+    return mk4(L, pdf);
+}
 template <bool COUNT>
 VT_DEV f4 evaluate_env(const Frame& F, f3 wi, Tally<COUNT>& tl)                      // lights.h:20-33
 {
-    const f3 L = background_color<COUNT>(F, wi, tl);
-    const float pdf = (F.use_image != 0) ? luminance(L) / F.env_integral : 1.0f / (4.0f * VT_PI);
-    return mk4(L, pdf);
+    return env_with_pdf(F, background_color<COUNT>(F, wi, tl));
 }
 template <bool COUNT>
 VT_DEV float cdf_u_at(const Frame& F, int x, int y, Tally<COUNT>& tl)
@@ -681,8 +684,11 @@ VT_DEV f4 evaluate_material(const Frame& F, int off, f3 wo, f3 wi, Tally<COUNT>&
     off += 1;
     switch (type) {
     case 0: { const f3 a = mat_vec(F, off + 3); return mk4(a / VT_PI, wi.y / VT_PI); }               // matte.h:1-10, lambertian.h:23-29
-    case 1: return eval_microfacet(mat_vec(F, off + 3), fetch_mat(F, off + 6), wo, wi);               // metal.h:1-17
-    case 2: return eval_microfacet(mk3(1.0f), fetch_mat(F, off + 6), wo, wi);                         // plastic.h:1-17
+    case 1:                                                                                            // metal.h:1-17
+    case 2: {                                                                                          // plastic.h:1-17 (reflectance 1)
+        const f3 refl = (type == 1) ? mat_vec(F, off + 3) : mk3(1.0f);
+        return eval_microfacet(refl, fetch_mat(F, off + 6), wo, wi);
+    }
     default: return mk4(0.f, 0.f, 0.f, 0.f);
     }
 }
@@ -692,20 +698,16 @@ VT_DEV f3 sample_material(const Frame& F, int off, f3 wo, int2& rng, f4& f_pdf, 
     const int type = f2i(fetch_mat(F, off));
     VT_TALLY(H, 1);
     off += 1;
-    switch (type) {
-    case 0: {                                                     // matte.h:12-22, lambertian.h:10-19
+    if ((unsigned)type > 2u) { f_pdf = mk4(0.f, 0.f, 0.f, 0.f); return mk3(0.0f); }    // unknown type: no rand() is consumed
+    const f4 u = rng_next<COUNT>(F, rng, tl);                     // one expansion for the three material types
+    if (type == 0) {                                              // matte.h:12-22, lambertian.h:10-19
         const f3 a = mat_vec(F, off + 3);
-        const f4 u = rng_next<COUNT>(F, rng, tl);
         const f4 l = cosine_hemisphere(u.x, u.y);
         f_pdf = mk4(a / VT_PI, l.w);
         return xyz(l);
     }
-    case 1: { const f4 u = rng_next<COUNT>(F, rng, tl);           // metal.h:19-36
-              return sample_microfacet(mat_vec(F, off + 3), fetch_mat(F, off + 6), wo, u.x, u.y, f_pdf); }
-    case 2: { const f4 u = rng_next<COUNT>(F, rng, tl);           // plastic.h:19-28
-              return sample_microfacet(mk3(1.0f), fetch_mat(F, off + 6), wo, u.x, u.y, f_pdf); }
-    default: f_pdf = mk4(0.f, 0.f, 0.f, 0.f); return mk3(0.0f);
-    }
+    const f3 refl = (type == 1) ? mat_vec(F, off + 3) : mk3(1.0f);   // metal.h:19-36; plastic.h:19-28 (reflectance 1)
+    return sample_microfacet(refl, fetch_mat(F, off + 6), wo, u.x, u.y, f_pdf);
 }
 template <bool COUNT>
 VT_DEV f3 emission_material(const Frame& F, int off, Tally<COUNT>& tl)                 // materials.h:46-56

@@ -458,9 +458,13 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, 
             const bool surface = (h.w & 3) != 0;
             bool finished = false;
             float4 a1 = make_float4(1.f, 1.f, 0.f, 0.f), a2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            // the environment seen by a ray that left the scene, primary (:187-208) or bounce (:282-289): ONE expansion of the
+            // lat-long mapping + bilinear lookup for both uses (this kernel is bound by instruction fetch, see vt_math.cuh)
+            f3 bg = mk3(0.0f);
+            if (!surface) bg = background_color<COUNT>(F, rd, tl);
             if (h.w & WF_HIT_PRIMARY) {
                 if (!surface) {                                                    // :187-194, :202-208
-                    radiance = background_color<COUNT>(F, rd, tl);
+                    radiance = bg;
                     finished = true;
                 } else if (!(0 < F.max_bounces)) finished = true;                  // :214 never entered
                 if (!finished) a2 = in.rad2[slot];                                 // a1 = throughput (1, 1), no pending light: the initialiser above
@@ -479,7 +483,7 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, 
                 }
                 if (!surface) {                                                    // :282-289 the bounce ray left the scene
                     const f3 throughput = mk3(a0.w, a1.x, a1.y);
-                    const f4 Lp = evaluate_env<COUNT>(F, rd, tl);
+                    const f4 Lp = env_with_pdf(F, bg);                                // lights.h:20-33
                     const float mis = power_heuristic(r1.z, Lp.w);
                     radiance = radiance + (throughput * xyz(Lp)) * mis;
                     finished = true;
