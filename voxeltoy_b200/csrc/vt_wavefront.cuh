@@ -264,9 +264,9 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
     const unsigned int slot = wf_reserve_rays(cnt, valid, want, false, slot_a, slot_b, sm);
     if (valid) {
         out.ray0[slot] = make_float4(ro.x, ro.y, ro.z, rd.x);
-        out.ray1[slot] = make_float4(rd.y, rd.z, 0.0f, i2f(0));
-        // radiance 0, throughput 1, nothing pending: wf_shade synthesises rad0 / rad1 for primary paths instead of reading them
-        out.rad2[slot] = make_float4(0.f, i2f(0), i2f(rng.x), i2f(rng.y));
+        // a primary path has radiance 0, throughput 1, nothing pending, bounce 0, no BSDF pdf: wf_shade synthesises all of that, and
+        // the only state there is -- the rng offset -- rides in the two unused words of ray1 (no rad0 / rad1 / rad2 traffic at all)
+        out.ray1[slot] = make_float4(rd.y, rd.z, i2f(rng.x), i2f(rng.y));
         out.pid[slot] = pid;
         if (!want) out.hit[slot] = make_int4(s.ix, s.iy, s.iz, flags);
     }
@@ -449,15 +449,16 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, 
             const float4 r0 = in.ray0[slot], r1 = in.ray1[slot];
             const float4 a0 = (h.w & WF_HIT_PRIMARY) ? make_float4(0.f, 0.f, 0.f, 1.0f) : in.rad0[slot];     // see wf_generate
             {   // gathers whose addresses are known now but whose values are needed hundreds of instructions later
-                const float4 a2p = in.rad2[slot];
-                const int nx = f2bits(a2p.z), ny = f2bits(a2p.w);
+                float2 rs = make_float2(r1.z, r1.w);                                // rng offset: in ray1 for primary paths (wf_generate)
+                if (!(h.w & WF_HIT_PRIMARY)) { const float4 a2p = in.rad2[slot]; rs = make_float2(a2p.z, a2p.w); }
+                const int nx = f2bits(rs.x), ny = f2bits(rs.y);
                 if ((unsigned)nx < (unsigned)F.noise_w && (unsigned)ny < (unsigned)F.noise_h) prefetch_l1(F.noise + ((size_t)nx + (size_t)ny * (size_t)F.noise_w));
                 if ((unsigned)h.x < (unsigned)V.X && (unsigned)h.y < (unsigned)V.Y && (unsigned)h.z < (unsigned)V.Z)
                     prefetch_l1(V.mat + ((size_t)h.x + (size_t)h.y * (size_t)V.X + (size_t)h.z * (size_t)V.X * (size_t)V.Y));
             }
             const f3 ro = mk3(r0.x, r0.y, r0.z), rd = mk3(r0.w, r1.x, r1.y);
             f3 radiance = mk3(a0.x, a0.y, a0.z);
-            int bounces = f2bits(r1.w);
+            int bounces = (h.w & WF_HIT_PRIMARY) ? 0 : f2bits(r1.w);
             const bool surface = (h.w & 3) != 0;
             bool finished = false;
             float4 a1 = make_float4(1.f, 1.f, 0.f, 0.f), a2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -470,7 +471,7 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, 
                     radiance = bg;
                     finished = true;
                 } else if (!(0 < F.max_bounces)) finished = true;                  // :214 never entered
-                if (!finished) a2 = in.rad2[slot];                                 // a1 = throughput (1, 1), no pending light: the initialiser above
+                a2 = make_float4(0.f, i2f(0), r1.z, r1.w);                         // a1 = throughput (1, 1), no pending light: the initialiser above
             } else {
                 a1 = in.rad1[slot]; a2 = in.rad2[slot];
                 // pathTracer.fs:248 with the shadow-ray result of the previous iteration
