@@ -51,7 +51,8 @@ constexpr int kWfGrab = 128;
 constexpr int kWfSkipMinLanes = 12;   // lanes that must want an empty-space skip before the warp pays for one          // rays a warp reserves per atomic on the hand-out counter
 
 enum { WF_RAY_SHADOW = 0, WF_RAY_BOUNCE = 1, WF_RAY_PRIMARY = 2 };
-enum { WF_HIT_VOXEL = 1, WF_HIT_GROUND = 2, WF_HIT_PRIMARY = 16 };    // hit.w flags (+ nanmask << 8)
+enum { WF_HIT_VOXEL = 1, WF_HIT_GROUND = 2, WF_HIT_PRIMARY = 16 };    // hit.w flags (+ nanmask << 8, + the path's bounce count << 16:
+                                                                      // wf_classify then needs no other word of the path state)
 
 // counts block of one iteration (device memory, zeroed once per batch)
 struct WfCounts {
@@ -362,8 +363,9 @@ wf_trace_kernel(const Volume V, const WfState S, const WfBuf out, WfCounts* __re
         }
         // ---- retire finished rays --------------------------------------------------------------------------
         if (have && status != DDA_RUNNING) {
-            if (type == WF_RAY_SHADOW) out.vis[pid] = wf_light_visible(V, aux, status, s);
-            else out.hit[pid] = make_int4(s.ix, s.iy, s.iz, wf_hit_flags(status, s) | (type == WF_RAY_PRIMARY ? WF_HIT_PRIMARY : 0));
+            const int kind = type & 3;                        // type >> 2: bounce count of the path, handed through to wf_classify
+            if (kind == WF_RAY_SHADOW) out.vis[pid] = wf_light_visible(V, aux, status, s);
+            else out.hit[pid] = make_int4(s.ix, s.iy, s.iz, wf_hit_flags(status, s) | (kind == WF_RAY_PRIMARY ? WF_HIT_PRIMARY : 0) | ((type >> 2) << 16));
             have = false;
         }
     }
@@ -391,7 +393,7 @@ wf_classify_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
             const int4 h = out.hit[i];
             const bool surface = (h.w & 3) != 0;
             const bool is_primary = (h.w & WF_HIT_PRIMARY) != 0;
-            const int bounces = is_primary ? -1 : f2bits(out.ray1[i].w);
+            const int bounces = is_primary ? -1 : (h.w >> 16);            // written next to the hit by wf_trace / wf_shade
             q = (surface && bounces + 1 < F.max_bounces) ? wf_material_queue(V, F, h.x, h.y, h.z) : 0;
             if (is_primary && surface && primary != nullptr) {
                 const unsigned int pid = out.pid[i];
@@ -548,10 +550,10 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, 
             out.ray0[tslot] = o_ray0; out.ray1[tslot] = o_ray1; out.rad0[tslot] = o_rad0; out.rad1[tslot] = o_rad1; out.rad2[tslot] = o_rad2;
             out.pid[tslot] = pid;
             if (st_a != DDA_RUNNING) out.vis[tslot] = wf_light_visible(V, target, st_a, sa);
-            if (st_b != DDA_RUNNING) out.hit[tslot] = make_int4(sb.ix, sb.iy, sb.iz, wf_hit_flags(st_b, sb));
+            if (st_b != DDA_RUNNING) out.hit[tslot] = make_int4(sb.ix, sb.iy, sb.iz, wf_hit_flags(st_b, sb) | (f2bits(o_ray1.w) << 16));
         }
         if (want_a) wf_store_ray(S, slot_a, sa, tslot, target, WF_RAY_SHADOW);
-        if (want_b) wf_store_ray(S, slot_b, sb, tslot, 0, WF_RAY_BOUNCE);
+        if (want_b) wf_store_ray(S, slot_b, sb, tslot, 0, WF_RAY_BOUNCE | (f2bits(o_ray1.w) << 2));
     }
     wf_flush_tally<COUNT>(tl, counters);
 }
