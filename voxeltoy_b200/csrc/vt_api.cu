@@ -805,7 +805,7 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
         if (batch >= lanes) VT_CUDA(c, cudaStreamWaitEvent(st, c->wf_acc[lane], 0));      // the lane's samples were folded in
         VT_CUDA(c, cudaMemsetAsync(cn, 0, sizeof(WfCounts) * (size_t)n_iters, st));
         { WfTimer t(c, VT_K_GENERATE, st);
-          wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 256), (unsigned)nb), 256, 0, st>>>(V, F, L, S, S.buf[0], pass0, cn, prim, c->d_counters); }
+          wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 256), (unsigned)std::min(nb, kWfGenRows)), 256, 0, st>>>(V, F, L, S, S.buf[0], pass0, nb, cn, prim, c->d_counters); }
         c->launches += 1;
         for (int it = 0; ; ++it) {
             // it == 0: primary rays; it >= 1: the shadow + bounce rays emitted by wf_shade(it)

@@ -475,6 +475,24 @@ VT_DEV void pinhole_ray(const Frame& F, f3 frag, float ux, float uy, f3& ro, f3&
     ro = xyz(o);
     rd = mk3(d.x / len, d.y / len, d.z / len);
 }
+// generateRay.h:30-101 (thin lens), split at its only sample-dependent input, the point on the lens: there is no pixel jitter in
+// this model, so the pixel's focal point (:60-84) is the same in every pass and wf_generate computes it once per pixel.
+VT_DEV f4 thin_lens_focal_point(const Frame& F, f3 frag)
+{
+    const float fd = F.shared->focal_distance;
+    const f3 es = xyz(screen_to_eye_persp(F, frag));
+    const f3 esd = normalize(es);
+    const float t = fd / -(esd.z);
+    const f3 focal = es + t * esd;
+    return mul44(F.inv_mv, focal.x, focal.y, focal.z, 1.0f);
+}
+VT_DEV void thin_lens_ray(const Frame& F, f4 fp, float ux, float uy, f3& ro, f3& rd)
+{
+    const f2 disk = sample_disk(ux, uy);
+    const f4 o = mul44(F.inv_mv, disk.x * F.lens_radius, disk.y * F.lens_radius, 0.0f, 1.0f);
+    ro = xyz(o);
+    rd = normalize(xyz(fp) - ro);
+}
 template <bool COUNT>
 VT_DEV void generate_ray(const Frame& F, f3 frag, int2& rng, f3& ro, f3& rd, Tally<COUNT>& tl)   // generateRay.h:104-123
 {
@@ -482,17 +500,8 @@ VT_DEV void generate_ray(const Frame& F, f3 frag, int2& rng, f3& ro, f3& rd, Tal
         const f4 u = rng_next<COUNT>(F, rng, tl);
         pinhole_ray(F, frag, u.x, u.y, ro, rd);
     } else if (F.lens_model == 1) {                               // generateRay.h:30-101
-        const float fd = F.shared->focal_distance;
         const f4 u = rng_next<COUNT>(F, rng, tl);
-        const f2 disk = sample_disk(u.x, u.y);
-        const f3 es = xyz(screen_to_eye_persp(F, frag));
-        const f3 esd = normalize(es);
-        const float t = fd / -(esd.z);
-        const f3 focal = es + t * esd;
-        const f4 fp = mul44(F.inv_mv, focal.x, focal.y, focal.z, 1.0f);
-        const f4 o = mul44(F.inv_mv, disk.x * F.lens_radius, disk.y * F.lens_radius, 0.0f, 1.0f);
-        ro = xyz(o);
-        rd = normalize(xyz(fp) - ro);
+        thin_lens_ray(F, thin_lens_focal_point(F, frag), u.x, u.y, ro, rd);
     } else {                                                      // generateRay.h:1-7
         const f4 e = screen_to_eye_ortho(F, frag);
         ro = xyz(mul44(F.inv_mv, e.x, e.y, e.z, e.w));

@@ -48,6 +48,7 @@ constexpr int kWfLiveMin = VT_WF_LIVE_MIN;        // refill the warp when fewer 
 #endif
 constexpr int kWfStepChunk = VT_WF_STEP_CHUNK;   // 3..16 measured: flat above 6 (refill checks amortised), 8 kept       // DDA iterations between two refill checks
 constexpr int kWfGrab = 128;
+constexpr int kWfGenRows = 8;         // thread rows of wf_generate: a thread generates every 8th pass of its pixel
 constexpr int kWfSkipMinLanes = 12;   // lanes that must want an empty-space skip before the warp pays for one          // rays a warp reserves per atomic on the hand-out counter
 
 enum { WF_RAY_SHADOW = 0, WF_RAY_BOUNCE = 1, WF_RAY_PRIMARY = 2 };
@@ -220,58 +221,68 @@ VT_DEV void wf_flush_tally(const Tally<COUNT>& tl, Counters* __restrict__ counte
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// wf_generate: pathTracer.fs:172-196 + dda.h:16-34 of the primary ray. grid = (n_items / 256, n_passes).
+// wf_generate: pathTracer.fs:172-196 + dda.h:16-34 of the primary ray. grid = (n_items / 256, min(n_passes, kWfGenRows)).
 // Every pixel of the frame gets a slot of generation 0; wf_classify routes the ones that miss the volume's box
 // to the finish queue.
 // ---------------------------------------------------------------------------------------------------------
 template <bool COUNT>
 VT_GLOBAL void __launch_bounds__(256)
-wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, const WfBuf out, int pass0,
+wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, const WfBuf out, int pass0, int n_batch,
                    WfCounts* __restrict__ cnt, int* __restrict__ primary, Counters* __restrict__ counters)
 {
     __shared__ WfBlockCounters sm;
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
-    const int pass_local = blockIdx.y;
-    const unsigned int pid = (unsigned)pass_local * (unsigned)S.n_items + (unsigned)item;
     Tally<COUNT> tl; tl.clear();
-    int px, py, status = DDA_NOHIT;
-    bool valid = false;
-    f3 ro = mk3(0.f), rd = mk3(0.f);
-    int2 rng = make_int2(0, 0);
-    int flags = WF_HIT_PRIMARY;
-    Dda s;
-    s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.sx = s.sy = s.sz = 1; s.dx = s.dy = s.dz = s.ex = s.ey = s.ez = 0.f;
-    if (item < S.n_items && wf_item_pixel(F, L, item, px, py)) {
-        valid = true;
-        const int sample = L.first_sample + (pass0 + pass_local) * L.sample_stride;
-        const f3 frag = mk3((float)px + 0.5f, (float)py + 0.5f, 0.55f);
-        rng = rng_offset(px, py, sample, F.noise_w, F.noise_h);                    // :174
-        generate_ray<COUNT>(F, frag, rng, ro, rd, tl);                             // :179
-        const float t = ray_aabb(ro, rd, V.bmin, V.bmax);                          // :183
-        if (!(t < 0.0f)) {
-            status = dda_begin<COUNT>(V, ro + t * rd, rd, s, tl);                  // :196-202
-            if (status != DDA_RUNNING) flags = wf_hit_flags(status, s) | WF_HIT_PRIMARY;
-        } else {
-            // :187-194 the ray misses the volume's box: finished here. Such pixels come in whole 8x4 blocks (the sky), so the
-            // warp does not diverge, and the path never costs a slot, a queue entry or a pass through wf_shade.
-            const f3 c = tonemap(background_color<COUNT>(F, rd, tl));
-            S.samples[pid] = make_float4(c.x, c.y, c.z, 1.0f);
-            valid = false;
+    int px = 0, py = 0;
+    const bool mine = item < S.n_items && wf_item_pixel(F, L, item, px, py);
+    const f3 frag = mk3((float)px + 0.5f, (float)py + 0.5f, 0.55f);
+    // thin lens: what does not depend on the sample is computed once per pixel for all the passes this thread generates
+    f4 lens_fp = mk4(0.f, 0.f, 0.f, 0.f);
+    if (mine && F.lens_model == 1) lens_fp = thin_lens_focal_point(F, frag);
+    // the passes of the batch are dealt to gridDim.y thread rows; every thread of a CTA runs the same number of iterations
+    for (int pass_local = blockIdx.y; pass_local < n_batch; pass_local += gridDim.y) {
+        const unsigned int pid = (unsigned)pass_local * (unsigned)S.n_items + (unsigned)item;
+        int status = DDA_NOHIT;
+        bool valid = false;
+        f3 ro = mk3(0.f), rd = mk3(0.f);
+        int2 rng = make_int2(0, 0);
+        int flags = WF_HIT_PRIMARY;
+        Dda s;
+        s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.sx = s.sy = s.sz = 1; s.dx = s.dy = s.dz = s.ex = s.ey = s.ez = 0.f;
+        if (mine) {
+            valid = true;
+            const int sample = L.first_sample + (pass0 + pass_local) * L.sample_stride;
+            rng = rng_offset(px, py, sample, F.noise_w, F.noise_h);                    // :174
+            if (F.lens_model == 1) {                                                   // :179, generateRay.h:30-101
+                const f4 u = rng_next<COUNT>(F, rng, tl);
+                thin_lens_ray(F, lens_fp, u.x, u.y, ro, rd);
+            } else generate_ray<COUNT>(F, frag, rng, ro, rd, tl);
+            const float t = ray_aabb(ro, rd, V.bmin, V.bmax);                          // :183
+            if (!(t < 0.0f)) {
+                status = dda_begin<COUNT>(V, ro + t * rd, rd, s, tl);                  // :196-202
+                if (status != DDA_RUNNING) flags = wf_hit_flags(status, s) | WF_HIT_PRIMARY;
+            } else {
+                // :187-194 the ray misses the volume's box: finished here. Such pixels come in whole 8x4 blocks (the sky), so the
+                // warp does not diverge, and the path never costs a slot, a queue entry or a pass through wf_shade.
+                const f3 c = tonemap(background_color<COUNT>(F, rd, tl));
+                S.samples[pid] = make_float4(c.x, c.y, c.z, 1.0f);
+                valid = false;
+            }
+            if (primary != nullptr && pass0 + pass_local == L.n_passes - 1) primary[(size_t)px + (size_t)py * (size_t)F.W] = -1;
         }
-        if (primary != nullptr && pass0 + pass_local == L.n_passes - 1) primary[(size_t)px + (size_t)py * (size_t)F.W] = -1;
+        unsigned int slot_a, slot_b;
+        const bool want = valid && status == DDA_RUNNING;
+        const unsigned int slot = wf_reserve_rays(cnt, valid, want, false, slot_a, slot_b, sm);
+        if (valid) {
+            out.ray0[slot] = make_float4(ro.x, ro.y, ro.z, rd.x);
+            // a primary path has radiance 0, throughput 1, nothing pending, bounce 0, no BSDF pdf: wf_shade synthesises all of that, and
+            // the only state there is -- the rng offset -- rides in the two unused words of ray1 (no rad0 / rad1 / rad2 traffic at all)
+            out.ray1[slot] = make_float4(rd.y, rd.z, i2f(rng.x), i2f(rng.y));
+            out.pid[slot] = pid;
+            if (!want) out.hit[slot] = make_int4(s.ix, s.iy, s.iz, flags);
+        }
+        if (want) wf_store_ray(S, slot_a, s, slot, 0, WF_RAY_PRIMARY);
     }
-    unsigned int slot_a, slot_b;
-    const bool want = valid && status == DDA_RUNNING;
-    const unsigned int slot = wf_reserve_rays(cnt, valid, want, false, slot_a, slot_b, sm);
-    if (valid) {
-        out.ray0[slot] = make_float4(ro.x, ro.y, ro.z, rd.x);
-        // a primary path has radiance 0, throughput 1, nothing pending, bounce 0, no BSDF pdf: wf_shade synthesises all of that, and
-        // the only state there is -- the rng offset -- rides in the two unused words of ray1 (no rad0 / rad1 / rad2 traffic at all)
-        out.ray1[slot] = make_float4(rd.y, rd.z, i2f(rng.x), i2f(rng.y));
-        out.pid[slot] = pid;
-        if (!want) out.hit[slot] = make_int4(s.ix, s.iy, s.iz, flags);
-    }
-    if (want) wf_store_ray(S, slot_a, s, slot, 0, WF_RAY_PRIMARY);
     wf_flush_tally<COUNT>(tl, counters);
 }
 
