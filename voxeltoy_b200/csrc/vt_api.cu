@@ -805,7 +805,8 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
         if (batch >= lanes) VT_CUDA(c, cudaStreamWaitEvent(st, c->wf_acc[lane], 0));      // the lane's samples were folded in
         VT_CUDA(c, cudaMemsetAsync(cn, 0, sizeof(WfCounts) * (size_t)n_iters, st));
         { WfTimer t(c, VT_K_GENERATE, st);
-          wf_generate_kernel<COUNT><<<dim3((unsigned)(n_items / 256), (unsigned)std::min(nb, kWfGenRows)), 256, 0, st>>>(V, F, L, S, S.buf[0], pass0, nb, cn, prim, c->d_counters); }
+          const int gen_x = n_items / 256, gen_rows = std::min(nb, std::max(1, (c->wf_sms * 8 + gen_x - 1) / gen_x));   // enough CTAs for every SM, else 1 row
+          wf_generate_kernel<COUNT><<<dim3((unsigned)gen_x, (unsigned)gen_rows), 256, 0, st>>>(V, F, L, S, S.buf[0], pass0, nb, cn, prim, c->d_counters); }
         c->launches += 1;
         for (int it = 0; ; ++it) {
             // it == 0: primary rays; it >= 1: the shadow + bounce rays emitted by wf_shade(it)

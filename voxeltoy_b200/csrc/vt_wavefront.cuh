@@ -48,7 +48,6 @@ constexpr int kWfLiveMin = VT_WF_LIVE_MIN;        // refill the warp when fewer 
 #endif
 constexpr int kWfStepChunk = VT_WF_STEP_CHUNK;   // 3..16 measured: flat above 6 (refill checks amortised), 8 kept       // DDA iterations between two refill checks
 constexpr int kWfGrab = 128;
-constexpr int kWfGenRows = 8;         // thread rows of wf_generate: a thread generates every 8th pass of its pixel
 constexpr int kWfSkipMinLanes = 12;   // lanes that must want an empty-space skip before the warp pays for one          // rays a warp reserves per atomic on the hand-out counter
 
 enum { WF_RAY_SHADOW = 0, WF_RAY_BOUNCE = 1, WF_RAY_PRIMARY = 2 };
@@ -221,7 +220,8 @@ VT_DEV void wf_flush_tally(const Tally<COUNT>& tl, Counters* __restrict__ counte
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// wf_generate: pathTracer.fs:172-196 + dda.h:16-34 of the primary ray. grid = (n_items / 256, min(n_passes, kWfGenRows)).
+// wf_generate: pathTracer.fs:172-196 + dda.h:16-34 of the primary ray. grid = (n_items / 256, rows): a thread generates every rows-th pass of its pixel;
+// rows = 1 whenever the frame alone fills the machine (1 / 2 / 4 / 8 / 16 rows measured at 1080p: 12.4 / 12.5 / 12.7 / 13.3 / 14.3 ms).
 // Every pixel of the frame gets a slot of generation 0; wf_classify routes the ones that miss the volume's box
 // to the finish queue.
 // ---------------------------------------------------------------------------------------------------------
