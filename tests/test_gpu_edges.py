@@ -78,3 +78,22 @@ def test_errors_are_reported_not_papered_over():
         ctx.close()
     with pytest.raises(vt.VtError):
         vt.Context(99)                                                     # no such device: there is no CPU path
+
+
+def test_custom_noise_tables(vt_ctx):
+    """vt_noise_upload with tables that are not 1024 x 1024: random.h:16-17 divides by the table's size, the kernels take shifts and
+    masks for powers of two and the literal signed division otherwise (negative offsets included: such samples read texel 0)."""
+    rng = np.random.default_rng(9)
+    vol = util.scene_fall_volume()
+    try:
+        for (h, w) in ((777, 1000), (32, 64), (1, 1), (2048, 512)):
+            noise = rng.random((h, w, 4), dtype=np.float32)
+            d = util.make_frame(vol, 96, 64, bounces=2, theta=120, phi=30)
+            d["noise"] = noise
+            vt_ctx.noise_upload(noise)
+            for variant in (2, 0):
+                vt_ctx.set_kernel_variant(variant)
+                _check(vt_ctx, d, 2)
+    finally:
+        vt_ctx.set_kernel_variant(2)
+        vt_ctx.noise_upload(None)

@@ -86,10 +86,22 @@ VT_DEV int wang_hash(int seed)                                   // random.h:3-1
     seed = seed ^ (seed >> 15);
     return seed;
 }
+// C / GLSL integer division and remainder (truncation toward zero, remainder with the sign of the dividend) by 2^k
+VT_DEV int div_pow2(int a, int k) { const unsigned m = (unsigned)(a >> 31); const unsigned q = (((unsigned)a ^ m) - m) >> k; return (int)((q ^ m) - m); }
+VT_DEV int rem_pow2(int a, int mask) { const unsigned m = (unsigned)(a >> 31); const unsigned r = (((unsigned)a ^ m) - m) & (unsigned)mask; return (int)((r ^ m) - m); }
+VT_DEV int2 rng_offset_from(int pixel_hash, int sequence, int rw, int rh)   // random.h:16-17 given hash(x + y * w)
+{
+    const int offset = pixel_hash ^ wang_hash(sequence);
+    // the noise table is 1024 x 1024 unless the caller uploaded another one: shifts and masks instead of three ~25-instruction
+    // signed divisions (same values for every int, negative offsets included)
+    if (rw > 0 && rh > 0 && (rw & (rw - 1)) == 0 && (rh & (rh - 1)) == 0)
+        return make_int2(rem_pow2(offset, rw - 1), rem_pow2(div_pow2(offset, __ffs(rw) - 1), rh - 1));
+    return make_int2(offset % rw, (offset / rw) % rh);
+}
+VT_DEV int rng_pixel_hash(int px, int py, int rw) { return wang_hash((int)((unsigned)px + (unsigned)py * (unsigned)rw)); }   // random.h:15
 VT_DEV int2 rng_offset(int px, int py, int sequence, int rw, int rh)   // random.h:13-18
 {
-    const int offset = wang_hash((int)((unsigned)px + (unsigned)py * (unsigned)rw)) ^ wang_hash(sequence);
-    return make_int2(offset % rw, (offset / rw) % rh);
+    return rng_offset_from(rng_pixel_hash(px, py, rw), sequence, rw, rh);
 }
 template <bool COUNT>
 VT_DEV f4 rng_next(const Frame& F, int2& off, Tally<COUNT>& tl)        // random.h:20-27

@@ -239,6 +239,7 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
     // thin lens: what does not depend on the sample is computed once per pixel for all the passes this thread generates
     f4 lens_fp = mk4(0.f, 0.f, 0.f, 0.f);
     if (mine && F.lens_model == 1) lens_fp = thin_lens_focal_point(F, frag);
+    const int pixel_hash = rng_pixel_hash(px, py, F.noise_w);                      // random.h:15, the same in every pass
     // the passes of the batch are dealt to gridDim.y thread rows; every thread of a CTA runs the same number of iterations
     for (int pass_local = blockIdx.y; pass_local < n_batch; pass_local += gridDim.y) {
         const unsigned int pid = (unsigned)pass_local * (unsigned)S.n_items + (unsigned)item;
@@ -252,7 +253,7 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
         if (mine) {
             valid = true;
             const int sample = L.first_sample + (pass0 + pass_local) * L.sample_stride;
-            rng = rng_offset(px, py, sample, F.noise_w, F.noise_h);                    // :174
+            rng = rng_offset_from(pixel_hash, sample, F.noise_w, F.noise_h);           // :174
             if (F.lens_model == 1) {                                                   // :179, generateRay.h:30-101
                 const f4 u = rng_next<COUNT>(F, rng, tl);
                 thin_lens_ray(F, lens_fp, u.x, u.y, ro, rd);
