@@ -49,8 +49,14 @@ constexpr int kWfLiveMin = VT_WF_LIVE_MIN;        // refill the warp when fewer 
 // DDA iterations between two refill checks. C2 trace ms per 256-spp step with the final 28-instruction step:
 // 6 / 8 / 10 / 12 / 14 / 16 / 20 / 24 iterations -> 88.3 / 84.4 / 82.5 / 81.2 / 82.1 / 81.0 / 84.0 / 84.6 (C3 and C4 also prefer 16)
 constexpr int kWfStepChunk = VT_WF_STEP_CHUNK;
-constexpr int kWfGrab = 128;          // rays a warp reserves per atomic on the hand-out counter
-constexpr int kWfSkipMinLanes = 12;   // lanes that must want an empty-space skip before the warp pays for one
+#ifndef VT_WF_GRAB
+#define VT_WF_GRAB 128
+#endif
+#ifndef VT_WF_SKIP_MIN_LANES
+#define VT_WF_SKIP_MIN_LANES 16
+#endif
+constexpr int kWfGrab = VT_WF_GRAB;                       // rays a warp reserves per atomic on the hand-out counter
+constexpr int kWfSkipMinLanes = VT_WF_SKIP_MIN_LANES;     // lanes that must want an empty-space skip (or half of the running ones) before the warp pays for one; C3 trace: 4 / 8 / 12 / 16+ -> 109.5 / 108.3 / 103.0 / 100.3 ms
 
 enum { WF_RAY_SHADOW = 0, WF_RAY_BOUNCE = 1, WF_RAY_PRIMARY = 2 };
 enum { WF_HIT_VOXEL = 1, WF_HIT_GROUND = 2, WF_HIT_PRIMARY = 16 };    // hit.w flags (+ nanmask << 8, + the path's bounce count << 16:
