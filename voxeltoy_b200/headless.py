@@ -23,7 +23,10 @@ def main(argv=None):
     except ValueError as e:
         print("headless: %s" % e, file=sys.stderr)
         return 1
-    print("paints=%d samples=%d status=%s" % (w.paints(), r.numberSamples(), r.getStatus()))
+    log = r.getLog().strip()
+    if log:
+        print(log)
+    print("paints=%d samples=%d resolution=%dx%d status=%s" % (w.paints(), r.numberSamples(), r.width, r.height, r.getStatus()))
     return 0
 
 

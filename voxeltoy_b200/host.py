@@ -413,6 +413,14 @@ class HeadlessWidget:
         self._L = lib(); self._r = renderer; self._h = self._L.vth_widget_create(renderer._h)
 
     def run(self, script):
+        # the repository keeps its scene fixtures gzip-ed: `vox` / `mesh` arguments go through plain_path like Renderer.loadVoxFile
+        lines = []
+        for line in script.split("\n"):
+            w = line.split("#")[0].split()
+            if len(w) >= 2 and w[0] in ("vox", "mesh"):
+                line = "%s %s" % (w[0], plain_path(w[1]))
+            lines.append(line)
+        script = "\n".join(lines)
         err = C.create_string_buffer(512)
         if self._L.vth_widget_run_script(self._h, script.encode(), err, 512) != 0:
             raise ValueError(err.value.decode())
