@@ -1,5 +1,5 @@
 """Developer timing script (not the contract bench): times vt_render on a few configurations with wall clock
-around vt_sync. Usage: python tools/quick_bench.py [config ...]"""
+around vt_sync. Usage: python tests/devtools/quick_bench.py [config ...]"""
 import os
 import sys
 import time

@@ -1,5 +1,5 @@
 """Developer timing script: voxelize bunny.obj at several resolutions (GPU ms = clear + scatter + derive, cudaEvents)
-and compare occupancy with the CPU oracle at sizes it finishes quickly. Usage: python tools/voxelize_bench.py [res ...]"""
+and compare occupancy with the CPU oracle at sizes it finishes quickly. Usage: python tests/devtools/voxelize_bench.py [res ...]"""
 import sys
 import time
 
