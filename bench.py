@@ -276,11 +276,11 @@ def main():
     trace_ms_per_launch = trace_ms / max(1, trace_launches)
     achieved = trace_bytes_per_launch / (trace_ms_per_launch * 1e-3) / 1e9
     step_achieved = bps * npx * PASSES / (ms_kernel * 1e-3) / 1e9     # every kernel of the step, all algorithmic bytes
-    # wf_trace is bound by instruction issue, so the ceiling that explains it is the issue rate: one DDA iteration is 28 SASS
+    # wf_trace is bound by instruction issue, so the ceiling that explains it is the issue rate: one DDA iteration is 27 SASS
     # instructions (cuobjdump of wf_trace_kernel), an SM issues 4 warp instructions per clock
     sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
-    issue_peak = sms * 4 * sm_hz / 28.0 * 32.0                         # DDA iterations per second with every lane stepping
+    issue_peak = sms * 4 * sm_hz / 27.0 * 32.0                         # DDA iterations per second with every lane stepping
     issue_achieved = steps_per_step * args.steps / (trace_ms * 1e-3) if trace_ms > 0 else 0.0
     kernel_ms_total = sum(v[0] for v in ktimes.values())
     # L2 read bandwidth of this GPU, measured now (the north star's roofline for this path is L2, not HBM: the grid, the noise
@@ -324,7 +324,7 @@ def main():
                                 "trace_frac": (achieved / l2_gbs) if l2_gbs else None, "step_frac": (step_achieved / l2_gbs) if l2_gbs else None},
                          "issue": {"achieved": issue_achieved / 1e9, "peak": issue_peak / 1e9, "unit": "G DDA iterations/s",
                                    "frac": issue_achieved / issue_peak,
-                                   "how": "wf_trace: counted DDA iterations / its device time vs SMs x 4 issue slots x SM clock / 28 "
+                                   "how": "wf_trace: counted DDA iterations / its device time vs SMs x 4 issue slots x SM clock / 27 "
                                           "instructions per iteration x 32 lanes"},
                          "note": "issue-bound, not bandwidth-bound: see profiles/ (issue slots busy, lanes per instruction)"},
         }

@@ -238,10 +238,22 @@ VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
     // :41-42 the bounds test is implied: outside the volume the occupancy bit is the sentinel (see Volume)
     const int key = (s.ix >> 2) + (s.iy >> 2) * V.BX + (s.iz >> 2) * V.BXY;
     if (key != s.bkey) { s.bkey = key; s.brick = __ldg(V.bricks + key); }
-    const int bit = (s.ix & 3) | ((s.iy & 3) << 2) | ((s.iz & 3) << 4);
-    unsigned int occ;      // low word of brick >> bit, kept opaque so that the test below stays a 32-bit one
-    asm("{ .reg .b64 t; shr.u64 t, %1, %2; cvt.u32.u64 %0, t; }" : "=r"(occ) : "l"(s.brick), "r"(bit));
-    if (occ & 1u) {                                               // :44-50, or the voxel is outside: :41-42
+    // the voxel's bit is moved to the SIGN position (shift left by 63 - bit; the complement folds into the three LOP3 that build the
+    // index), so the test is one compare instead of AND + compare; kept opaque so that nvcc does not turn it back
+    // nbit = 63 - ((x&3) | (y&3)<<2 | (z&3)<<4) = (~x & 3) | (~y & 3)<<2 | (~z & 3)<<4, with (~v) << k written as v * -2^k - 2^k
+    int occ;
+    asm("{\n\t"
+        ".reg .b64 t;\n\t"
+        ".reg .b32 lo, ty, tz, n;\n\t"
+        "mad.lo.s32 ty, %3, -4, -4;\n\t"
+        "mad.lo.s32 tz, %4, -16, -16;\n\t"
+        "lop3.b32 n, %2, 3, 0, 0x0c;\n\t"          // ~x & 3
+        "lop3.b32 n, n, 0x30, tz, 0xf8;\n\t"       // n | (0x30 & tz)
+        "lop3.b32 n, n, 0xc, ty, 0xf8;\n\t"        // n | (0xc & ty)
+        "shl.b64 t, %1, n;\n\t"
+        "mov.b64 {lo, %0}, t;\n\t"
+        "}" : "=r"(occ) : "l"(s.brick), "r"(s.ix), "r"(s.iy), "r"(s.iz));
+    if (occ < 0) {                                                // :44-50, or the voxel is outside: :41-42
         const bool inside = (unsigned)s.ix < (unsigned)V.X && (unsigned)s.iy < (unsigned)V.Y && (unsigned)s.iz < (unsigned)V.Z;
         if (inside) VT_TALLY(S, 1);
         return inside ? DDA_HIT : DDA_NOHIT;
