@@ -290,12 +290,21 @@ def main():
     except Exception:
         l2_gbs = None
     traffic = None
+    shade_traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("wf_trace_kernel_dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("wf_trace_kernel_dram_bytes_per_launch")
+            shade_traffic = tj.get("wf_shade_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # the runner-up (a near tie with wf_trace): wf_shade, whose algorithmic bytes are everything of SURVEY 8(d) except the
+    # DDA words and the accumulator: 16 R + 36 H + 4 E + 64 Q
+    shade_ms, shade_launches = ktimes["shade"]
+    shade_bytes_step = (16 * cnt["rand_calls"] + 36 * cnt["material_evals"] + 4 * cnt["cdf_loads"] + 64 * cnt["env_lookups"]) / float(n_count)
+    shade_bytes_per_launch = shade_bytes_step * args.steps / max(1, shade_launches)
+    shade_achieved = shade_bytes_per_launch / (shade_ms / max(1, shade_launches) * 1e-3) / 1e9 if shade_ms > 0 else 0.0
 
     if rank == 0:
         line = {
@@ -322,6 +331,11 @@ def main():
                                         "Q": cnt["env_lookups"] / n_samp},
                          "l2": {"peak": l2_gbs, "unit": "GB/s", "how": "measured live: 48 MiB buffer, ld.global.cg 16 B, 148x8 CTAs, best of 3",
                                 "trace_frac": (achieved / l2_gbs) if l2_gbs else None, "step_frac": (step_achieved / l2_gbs) if l2_gbs else None},
+                         "runner_up": {"kernel": "wf_shade_kernel", "bound": "hbm", "achieved": shade_achieved, "peak": peak, "unit": "GB/s",
+                                       "frac": shade_achieved / peak, "traffic": shade_traffic,
+                                       "algorithmic_bytes_per_launch": shade_bytes_per_launch,
+                                       "ms_per_launch": shade_ms / max(1, shade_launches),
+                                       "share_of_step": shade_ms / kernel_ms_total if kernel_ms_total else None},
                          "issue": {"achieved": issue_achieved / 1e9, "peak": issue_peak / 1e9, "unit": "G DDA iterations/s",
                                    "frac": issue_achieved / issue_peak,
                                    "how": "wf_trace: counted DDA iterations / its device time vs SMs x 4 issue slots x SM clock / 27 "
