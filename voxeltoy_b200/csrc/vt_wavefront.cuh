@@ -180,14 +180,20 @@ VT_DEV void wf_enqueue(const WfState& S, WfCounts* __restrict__ cnt, int q, unsi
 
 // reserve one trace-list entry per thread with `traced` and one ray-queue slot per set predicate.
 // Returns the trace-list slot; slot_a / slot_b are valid where want_a / want_b.
+// once per kernel, before the first wf_reserve_rays
+VT_DEV void wf_reserve_init(WfBlockCounters& sm)
+{
+    if (threadIdx.x < 2) sm.cnt[kWfQueues + threadIdx.x] = 0u;
+    __syncthreads();
+}
 VT_DEV unsigned int wf_reserve_rays(WfCounts* __restrict__ cnt, bool traced, bool want_a, bool want_b, unsigned int& slot_a, unsigned int& slot_b,
                                     WfBlockCounters& sm)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    if (threadIdx.x < 2) sm.cnt[kWfQueues + threadIdx.x] = 0u;
-    __syncthreads();
+    // sm.cnt[kWfQueues .. +1] are zero on entry: wf_reserve_init at kernel start, then thread 0 re-zeroes them below (two barriers
+    // per call instead of three)
     const unsigned mt = __ballot_sync(full, traced), ma = __ballot_sync(full, want_a), mb = __ballot_sync(full, want_b);
     unsigned int wt = 0, wr = 0;
     if (mt != 0u) {
@@ -198,6 +204,7 @@ VT_DEV unsigned int wf_reserve_rays(WfCounts* __restrict__ cnt, bool traced, boo
     if (threadIdx.x == 0 && sm.cnt[kWfQueues] != 0u) {
         const unsigned long long b = atomicAdd(&cnt->tq_rq, (unsigned long long)sm.cnt[kWfQueues] | ((unsigned long long)sm.cnt[kWfQueues + 1] << 32));
         sm.base[kWfQueues] = (unsigned int)b; sm.base[kWfQueues + 1] = (unsigned int)(b >> 32);
+        sm.cnt[kWfQueues] = 0u; sm.cnt[kWfQueues + 1] = 0u;                 // ready for the next call (visible after the barrier below)
     }
     __syncthreads();
     const unsigned int rbase = sm.base[kWfQueues + 1] + wr;
@@ -239,6 +246,7 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
                    WfCounts* __restrict__ cnt, int* __restrict__ primary, Counters* __restrict__ counters)
 {
     __shared__ WfBlockCounters sm;
+    wf_reserve_init(sm);
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     Tally<COUNT> tl; tl.clear();
     int px = 0, py = 0;
@@ -438,6 +446,7 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const WfBuf in, 
                 Counters* __restrict__ counters)
 {
     __shared__ WfBlockCounters sm;
+    wf_reserve_init(sm);
     const int lane = threadIdx.x & 31;
     const int warps_per_cta = blockDim.x >> 5;
     Tally<COUNT> tl; tl.clear();
