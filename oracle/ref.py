@@ -31,6 +31,7 @@ def lib():
         S = C.POINTER(vto.Scene)
         L.vtref_describe.restype = C.c_char_p
         L.vtref_render_pass.argtypes = [S, C.c_int, f32p, C.c_int]
+        L.vtref_render_pixels.argtypes = [S, C.c_int, i32p, C.c_size_t, f32p, C.c_int]
         L.vtref_preview_pass.argtypes = [S, C.c_int, f32p, C.c_int]
         L.vtref_pick.argtypes = [S, C.c_float, C.c_float, C.c_float, f32p, i32p, f32p]
         L.vtref_pick_focal.argtypes = [S, C.c_float, C.c_float]; L.vtref_pick_focal.restype = C.c_float
@@ -61,6 +62,14 @@ def render_pass(scene, sample_count, n_threads=None):
     """integrator/pathTracer.fs over the whole frame: (H, W, 4) float32, row 0 = bottom row."""
     out = np.empty((scene.H, scene.W, 4), np.float32)
     lib().vtref_render_pass(C.byref(scene), int(sample_count), _fp(out), int(n_threads or os.cpu_count() or 1))
+    return out
+
+
+def render_pixels(scene, sample_count, xy, n_threads=None):
+    """pathTracer.fs at the listed (x, y) fragments only: (n, 4) float32."""
+    xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+    out = np.empty((xy.shape[0], 4), np.float32)
+    lib().vtref_render_pixels(C.byref(scene), int(sample_count), _ip(xy), xy.shape[0], _fp(out), int(n_threads or os.cpu_count() or 1))
     return out
 
 

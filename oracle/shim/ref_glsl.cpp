@@ -100,6 +100,27 @@ void vtref_render_pass(const vto_scene* s, int sample_count, float* out_rgba, in
     run_fullscreen(sh, s, out_rgba, n_threads);
 }
 
+// K1 on a list of pixels (x, y pairs): the same shader invocation as the full-screen quad would run at those fragments
+void vtref_render_pixels(const vto_scene* s, int sample_count, const int32_t* xy, size_t n, float* out_rgba, int n_threads)
+{
+    PathTracerFS proto;
+    bind_integrator(proto, s, sample_count);
+    proto.materialDataTexture.p = s->materials;
+    proto.emissiveVoxelIndicesTexture.p = s->emissive; proto.emissiveVoxelIndicesTexture.n = s->n_emissive;
+    proto.pathtracerMaxNumBounces = s->max_bounces;
+    #pragma omp parallel num_threads(n_threads > 0 ? n_threads : omp_get_max_threads())
+    {
+        PathTracerFS sh = proto;
+        #pragma omp for schedule(dynamic, 64)
+        for (long i = 0; i < (long)n; ++i) {
+            sh.gl_FragCoord = vec4((float)xy[2 * i] + 0.5f, (float)xy[2 * i + 1] + 0.5f, 0.55f, 1.0f);
+            sh.main();
+            float* o = out_rgba + 4 * (size_t)i;
+            o[0] = sh.outColor.x; o[1] = sh.outColor.y; o[2] = sh.outColor.z; o[3] = sh.outColor.w;
+        }
+    }
+}
+
 // K4: integrator/editMode.fs
 void vtref_preview_pass(const vto_scene* s, int sample_count, float* out_rgba, int n_threads)
 {

@@ -793,6 +793,25 @@ void vto_render_pass(const vto_scene* s, int sample_count, float* out_rgba,
     }
 }
 
+/* K1 on an explicit list of pixels (x, y pairs): the same trace_pixel as vto_render_pass, for comparisons of crops and
+ * strided subsets of frames whose full size the CPU cannot render in test time. out_rgba: 4 floats per listed pixel. */
+void vto_render_pixels(const vto_scene* s, int sample_count, const int32_t* xy, size_t n, float* out_rgba,
+                       int32_t* primary_hit, int n_threads)
+{
+    long i;
+    if (n_threads < 1) n_threads = 1;
+#pragma omp parallel num_threads(n_threads)
+    {
+        ctx_t c;
+        ctx_init(&c, s);
+#pragma omp for schedule(dynamic, 64)
+        for (i = 0; i < (long)n; i++) {
+            v4 o = trace_pixel(&c, xy[2 * i], xy[2 * i + 1], sample_count, primary_hit ? &primary_hit[i] : NULL);
+            out_rgba[4 * i + 0] = o.x; out_rgba[4 * i + 1] = o.y; out_rgba[4 * i + 2] = o.z; out_rgba[4 * i + 3] = o.w;
+        }
+    }
+}
+
 /* integrator/editMode.fs:62-142 */
 static v4 preview_pixel(ctx_t* c, int px, int py, int sample_count)
 {

@@ -89,6 +89,10 @@ void vto_volume_bounds(int X, int Y, int Z, float bmin[3], float bmax[3], float 
 void vto_render_pass(const vto_scene* s, int sample_count, float* out_rgba,
                      int32_t* primary_hit, int32_t* steps, vto_counters* counters, int n_threads);
 
+/* K1 on a list of n pixels (xy: n pairs); out_rgba: 4 floats per pixel, primary_hit optional (n) */
+void vto_render_pixels(const vto_scene* s, int sample_count, const int32_t* xy, size_t n, float* out_rgba,
+                       int32_t* primary_hit, int n_threads);
+
 /* K4: integrator/editMode.fs */
 void vto_preview_pass(const vto_scene* s, int sample_count, float* out_rgba, int n_threads);
 

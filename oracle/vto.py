@@ -59,6 +59,7 @@ def lib():
     L = C.CDLL(path)
     L.vto_volume_bounds.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, f32p]
     L.vto_render_pass.argtypes = [C.POINTER(Scene), C.c_int, f32p, i32p, i32p, C.POINTER(Counters), C.c_int]
+    L.vto_render_pixels.argtypes = [C.POINTER(Scene), C.c_int, i32p, C.c_size_t, f32p, i32p, C.c_int]
     L.vto_preview_pass.argtypes = [C.POINTER(Scene), C.c_int, f32p, C.c_int]
     L.vto_accumulate.argtypes = [f32p, f32p, C.c_int, C.c_size_t]
     L.vto_voxelize.argtypes = [f32p, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t, f32p,
@@ -189,6 +190,15 @@ def render_pass(scene, sample_count, n_threads=None, want_hits=True, want_steps=
     lib().vto_render_pass(C.byref(scene), sample_count, _fp(out), _ip(hits), _ip(steps), C.byref(cnt), n_threads)
     counters = {k: getattr(cnt, k) for k, _ in Counters._fields_}
     return out, hits, steps, counters
+
+
+def render_pixels(scene, sample_count, xy, n_threads=None, want_hits=False):
+    """trace_pixel on the listed (x, y) pixels only: (n, 4) float32 (+ (n,) primary hits)."""
+    xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+    out = np.empty((xy.shape[0], 4), np.float32)
+    hits = np.empty(xy.shape[0], np.int32) if want_hits else None
+    lib().vto_render_pixels(C.byref(scene), int(sample_count), _ip(xy), xy.shape[0], _fp(out), _ip(hits), n_threads or os.cpu_count() or 1)
+    return (out, hits) if want_hits else out
 
 
 def preview_pass(scene, sample_count, n_threads=None):

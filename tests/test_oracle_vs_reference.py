@@ -106,3 +106,17 @@ def test_voxelizer_random_and_degenerate_triangles():
     for res in ((16, 16, 16), (40, 40, 40)):
         a = vto.voxelize(verts, idx, M, res); b = ref.voxelize(verts, idx, M, res)
         assert np.array_equal(a, b), "%d voxels differ" % int((a != b).sum())
+
+
+def test_render_pixels_equals_full_frame_both_sides():
+    """The pixel-list entry points used by the full-size GPU tests (C5 at 4K) are the same shader invocations as the
+    full-screen pass: oracle == reference GLSL == the corresponding pixels of a full frame."""
+    d = util.make_frame(util.mixed_scene(), 200, 120, bounces=5, theta=130, phi=25, lens_model=1, fstop=2.0, focal_distance=500.0)
+    s = vto.make_scene(d)
+    full, hits, _, _ = vto.render_pass(s, 3)
+    ys, xs = np.mgrid[0:120:7, 0:200:5]
+    xy = np.stack([xs.ravel(), ys.ravel()], 1)
+    a, h = vto.render_pixels(s, 3, xy, want_hits=True)
+    _same(a, full[xy[:, 1], xy[:, 0]])
+    assert np.array_equal(h, hits[xy[:, 1], xy[:, 0]])
+    _same(ref.render_pixels(s, 3, xy), a)
