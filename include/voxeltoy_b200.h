@@ -152,9 +152,9 @@ int vt_set_partition(vt_ctx* ctx, int mode, int rank, int world);
 /* sample-partition mode keeps a running SUM instead of an average; expose the device buffer so the caller's
  * collective (NCCL through torch.distributed) can reduce it in place. W*H float4. */
 void* vt_accum_device_ptr(vt_ctx* ctx);
-/* render kernel variant: 0 = one-thread-per-pixel megakernel, 1 = persistent per-lane path state machine (measured
- * slower, kept for the comparison in DESIGN.md), 2 = wavefront with per-material shade queues and self-refilling
- * trace warps (default); all variants produce identical bits */
+/* render kernel variant: 0 = one-thread-per-pixel megakernel, 2 = wavefront with per-material shade queues and
+ * self-refilling trace warps (default); both produce identical bits (1 was round 1's per-lane state machine: removed,
+ * measured slower) */
 int vt_set_kernel_variant(vt_ctx* ctx, int variant);
 /* wavefront variant: upper bound on the paths (pixel-passes) in flight per batch; the passes of one vt_render call are
  * split into batches of floor(max_paths / pixels) passes (at least 1). Tuning knob, no effect on results. */
@@ -168,7 +168,7 @@ int vt_set_empty_skip(vt_ctx* ctx, int mode);
 /* device time of the wavefront kernels by kind, measured with cudaEvent pairs around every launch on the context's
  * stream while enabled; vt_get_kernel_times synchronises, returns the sums since the last call and clears them.
  * (the reference's only timer is the per-frame GL_TIMESTAMP pair of timer/gpuTimer.cpp:33-69) */
-enum { VT_K_GENERATE = 0, VT_K_TRACE = 1, VT_K_CLASSIFY = 2, VT_K_SHADE = 3, VT_K_ACCUMULATE = 4, VT_K_COUNT = 5 };
+enum { VT_K_GENERATE = 0, VT_K_TRACE = 1, VT_K_OTHER = 2, VT_K_SHADE = 3, VT_K_ACCUMULATE = 4, VT_K_COUNT = 5 };
 typedef struct vt_kernel_times { float ms[VT_K_COUNT]; uint32_t launches[VT_K_COUNT]; } vt_kernel_times;
 int vt_kernel_timing_enable(vt_ctx* ctx, int enable);
 int vt_get_kernel_times(vt_ctx* ctx, vt_kernel_times* out);

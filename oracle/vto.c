@@ -627,7 +627,7 @@ static v3 direct_lighting(ctx_t* c, int mat_off, const basis_t* hb, v3 wo, iv2* 
     v4 bf; float mis, adot;
 
     if (sampling_voxel) {
-        int eidx = s->emissive[light_index];                                   /* :85 */
+        int eidx = ((unsigned)light_index < (unsigned)s->n_emissive) ? s->emissive[light_index] : 0;   /* :85 texelFetch, out of range -> 0 */
         int eoff; v3 ep, toL, vse; float r, area, jac; basis_t lb;
         voxel_index_to_pos(eidx, s->X, s->Y, &ex, &ey, &ez);                   /* :86 */
         eoff = fetch_offset(s, ex, ey, ez);                                    /* :87 */

@@ -65,7 +65,7 @@ def test_errors_are_reported_not_papered_over():
         with pytest.raises(vt.VtError):
             ctx.set_partition(vt.VT_PART_TILES, 3, 2)
         with pytest.raises(vt.VtError):
-            ctx.set_kernel_variant(7)
+            ctx.set_kernel_variant(1)                                       # round 1's per-lane state machine: removed
         with pytest.raises(vt.VtError):
             ctx.voxelize(np.zeros((3, 3), np.float32), np.array([0, 1, 5], np.uint32), np.eye(4, dtype=np.float32), (8, 8, 8))
         t = scenes.MaterialTable(); t.lambert((0.5, 0.5, 0.5))

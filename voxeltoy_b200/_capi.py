@@ -316,7 +316,7 @@ class Context:
     def set_kernel_variant(self, variant):
         self._ck(self.lib.vt_set_kernel_variant(self.h, int(variant)))
 
-    KERNEL_KINDS = ("generate", "trace", "classify", "shade", "accumulate")
+    KERNEL_KINDS = ("generate", "trace", "other", "shade", "accumulate")
 
     def kernel_timing_enable(self, on):
         self._ck(self.lib.vt_kernel_timing_enable(self.h, 1 if on else 0))

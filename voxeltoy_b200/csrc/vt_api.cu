@@ -3,7 +3,6 @@
 // kernels of vt_kernels.cuh. No OpenGL, no CPU fallback: every compute entry point
 // needs a live CUDA context and fails with VT_ERR_CUDA / VT_ERR_NO_DEVICE otherwise.
 #include "../../include/voxeltoy_b200.h"
-#include "vt_pathstate.cuh"
 #include "vt_wavefront.cuh"
 #include "vt_env.cuh"
 
@@ -61,9 +60,8 @@ struct vt_ctx {
     int* d_result = nullptr;
     // partition
     int part_mode = VT_PART_NONE, part_rank = 0, part_world = 1;
-    // render kernel variant: 0 = one-thread-per-pixel megakernel (default), 1 = persistent per-lane path state machine
-    // 2 = wavefront (vt_wavefront.cuh, default for the path tracer)
-    int variant = 2; unsigned int* d_work = nullptr; int ps_blocks[2] = {0, 0};
+    // render kernel variant: 0 = one-thread-per-pixel megakernel, 2 = wavefront (vt_wavefront.cuh, default for the path tracer)
+    int variant = 2;
     // wavefront state (variant 2): SoA path state + queues, sized for wf_capacity paths
     // Batches run on up to kWfLanes internal streams ("lanes"), each with its own state pool, so the ramp-down tail of one
     // batch's kernels is filled by the other's CTAs; accumulation stays on the caller's stream, in pass order.
@@ -73,7 +71,8 @@ struct vt_ctx {
     WfCounts* d_wf_counts[kWfLanes] = {nullptr, nullptr, nullptr, nullptr}; int wf_counts_cap[kWfLanes] = {0, 0, 0, 0};
     cudaStream_t wf_stream[kWfLanes] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t wf_fork = nullptr, wf_done[kWfLanes] = {nullptr, nullptr, nullptr, nullptr}, wf_acc[kWfLanes] = {nullptr, nullptr, nullptr, nullptr};
-    size_t wf_max_paths = (size_t)128 << 20;   // paths in flight per batch: 340 B each -> <= 45.6 GB of the 180 GB (C2: 32 -> 64 -> 128 Mi = 2 542 -> 2 582 -> 2 607 Msamples/s)
+    size_t wf_max_paths = (size_t)128 << 20;   // paths in flight per batch: 324 B each -> <= 43.5 GB of the 180 GB (C2, round 1: 32 -> 64 -> 128 Mi = 2 542 -> 2 582 -> 2 607 Msamples/s)
+    size_t wf_queue_slack = 0;                 // queue entries beyond the path count: the chunked reservations of wf_trace
     int wf_shade_blocks[2] = {0, 0}, wf_trace_blocks[2] = {0, 0}, wf_sms = 0;
     // per-kernel device timing (vt_kernel_timing_enable): event pairs around every wavefront launch
     bool timing = false;
@@ -142,13 +141,13 @@ int vt_create(int device, vt_ctx** out)
     if (const char* e = getenv("VT_WF_MAX_PATHS")) { const long long v = atoll(e); if (v > 0) c->wf_max_paths = (size_t)v; }   // tuning knob
     if (const char* e = getenv("VT_EMPTY_SKIP")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->skip_mode = v; }
     if (const char* e = getenv("VT_WF_LANES")) { const int v = atoi(e); if (v >= 1 && v <= vt_ctx::kWfLanes) c->wf_lanes = v; }
-    if (const char* e = getenv("VT_KERNEL_VARIANT")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->variant = v; }
+    if (const char* e = getenv("VT_KERNEL_VARIANT")) { const int v = atoi(e); if (v == 0 || v == 2) c->variant = v; }
     Shared sh;
     sh.focal_distance = 99999999.0f;                                  // renderer.cpp:712-720
     sh.sel_index[0] = sh.sel_index[1] = sh.sel_index[2] = sh.sel_index[3] = 0;   // :723-737
     sh.sel_normal[0] = 1.f; sh.sel_normal[1] = sh.sel_normal[2] = sh.sel_normal[3] = 0.f;
     if (cudaMalloc(&c->d_shared, sizeof(Shared)) != cudaSuccess || cudaMalloc(&c->d_result, 4 * sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&c->d_counters, sizeof(Counters)) != cudaSuccess || cudaMalloc(&c->d_work, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&c->d_counters, sizeof(Counters)) != cudaSuccess ||
         cudaMemcpy(c->d_shared, &sh, sizeof sh, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemset(c->d_counters, 0, sizeof(Counters)) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
@@ -183,7 +182,7 @@ void vt_destroy(vt_ctx* c)
     if (c->wf_fork) cudaEventDestroy(c->wf_fork);
     for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
-    cudaFree(c->d_primary); cudaFree(c->d_work); cudaFree(c->d_shared); cudaFree(c->d_result); cudaFree(c->d_counters);
+    cudaFree(c->d_primary); cudaFree(c->d_shared); cudaFree(c->d_result); cudaFree(c->d_counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -372,7 +371,7 @@ int vt_get_volume_info(vt_ctx* c, int32_t res[3], float bmin[3], float bmax[3], 
 int vt_noise_upload(vt_ctx* c, const float* rgba, int w, int h)
 {
     if (!c) return VT_ERR_INVALID;
-    VT_REQ(c, w > 0 && h > 0, "bad noise size");
+    VT_REQ(c, w > 0 && h > 0 && (size_t)w * (size_t)h <= ((size_t)1 << 29), "bad noise size (the table may hold at most 2^29 texels)");
     VT_BIND(c);
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
     std::vector<float> gen;
@@ -669,7 +668,7 @@ int vt_set_partition(vt_ctx* c, int mode, int rank, int world)
 int vt_set_kernel_variant(vt_ctx* c, int variant)
 {
     if (!c) return VT_ERR_INVALID;
-    VT_REQ(c, variant >= 0 && variant <= 2, "kernel variant must be 0 (megakernel), 1 (persistent path state machine) or 2 (wavefront)");
+    VT_REQ(c, variant == 0 || variant == 2, "kernel variant must be 0 (megakernel) or 2 (wavefront)");
     c->variant = variant;
     return VT_OK;
 }
@@ -721,6 +720,10 @@ int vt_counters_enable(vt_ctx* c, int enable) { if (!c) return VT_ERR_INVALID; c
 } // extern "C" (the wavefront driver is a template)
 
 // ---- wavefront driver (variant 2, vt_wavefront.cuh) -------------------------------------------------------
+// bytes of wavefront storage per path in flight: 2 generations of 64-byte path records, 2 regions of 40-byte ray records, the
+// sample, 5 shade queues of 20-byte entries, 1 visibility bit
+static constexpr size_t kWfBytesPerPath = 2 * 64 + 2 * 40 + 16 + kWfQueues * 20;
+
 static int wf_reserve(vt_ctx* c, int lane, size_t n_paths, int n_iters)
 {
     if (!c->wf_stream[lane]) {
@@ -732,22 +735,19 @@ static int wf_reserve(vt_ctx* c, int lane, size_t n_paths, int n_iters)
     if (n_paths > c->wf_capacity[lane]) {
         VT_CUDA(c, cudaDeviceSynchronize());
         cudaFree(c->d_wf_pool[lane]); c->d_wf_pool[lane] = nullptr; c->wf_capacity[lane] = 0;
-        // per path: 2 generations x (5 x 16 B state + 16 B hit + vis + pid), sample, 2 x 48-byte ray records, 5 queues: 340 bytes
-        const size_t bytes = n_paths * (2 * (5 * 16 + 16 + 4 + 4) + 16 + 2 * 48 + kWfQueues * 4);
-        VT_CUDA(c, cudaMalloc(&c->d_wf_pool[lane], bytes));
+        const size_t n_pad = (n_paths + 63) & ~(size_t)63;                  // keeps every sub-array 256-byte aligned
+        const size_t n_queue = n_pad + c->wf_queue_slack;
+        const size_t bytes = n_pad * (2 * 64 + 2 * 40 + 16) + n_queue * kWfQueues * 20 + ((n_pad + 2047) / 2048) * 256 + 4096;
+        const cudaError_t e = cudaMalloc(&c->d_wf_pool[lane], bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, VT_ERR_CUDA, "wavefront pool of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
         char* p = (char*)c->d_wf_pool[lane];
-        auto take = [&](size_t b) { char* r = p; p += b; return (void*)r; };
+        auto take = [&](size_t b) { char* r = p; p += (b + 255) & ~(size_t)255; return (void*)r; };
         WfState& W = c->wf[lane];
-        for (int g = 0; g < 2; ++g) {
-            WfBuf& B = W.buf[g];
-            B.ray0 = (float4*)take(n_paths * 16); B.ray1 = (float4*)take(n_paths * 16);
-            B.rad0 = (float4*)take(n_paths * 16); B.rad1 = (float4*)take(n_paths * 16); B.rad2 = (float4*)take(n_paths * 16);
-            B.hit = (int4*)take(n_paths * 16);
-        }
-        W.samples = (float4*)take(n_paths * 16);
-        W.rq0 = (int4*)take(n_paths * 32); W.rq1 = (float4*)take(n_paths * 32); W.rq2 = (float4*)take(n_paths * 32);
-        for (int g = 0; g < 2; ++g) { W.buf[g].vis = (int*)take(n_paths * 4); W.buf[g].pid = (unsigned int*)take(n_paths * 4); }
-        for (int k = 0; k < kWfQueues; ++k) W.sq[k] = (unsigned int*)take(n_paths * 4);
+        for (int g = 0; g < 2; ++g) W.state[g] = (float4*)take(n_pad * 64);
+        for (int r = 0; r < 2; ++r) { W.rq_a[r] = (int4*)take(n_pad * 16); W.rq_b[r] = (float4*)take(n_pad * 16); W.rq_c[r] = (float2*)take(n_pad * 8); }
+        W.samples = (float4*)take(n_pad * 16);
+        for (int k = 0; k < kWfQueues; ++k) { W.sq[k] = (int4*)take(n_queue * 16); W.sq_rng[k] = (int*)take(n_queue * 4); }
+        W.vis = (unsigned int*)take(((n_pad + 2047) / 2048) * 256);
         c->wf_capacity[lane] = n_paths;
     }
     if (n_iters > c->wf_counts_cap[lane]) {
@@ -773,7 +773,7 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
     if (c->wf_shade_blocks[ci] == 0) {
         int per_sm_s = 0, per_sm_t = 0, sms = 0;
         VT_CUDA(c, wf_shade_blocks_per_sm(COUNT, &per_sm_s));
-        VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, wf_trace_kernel<COUNT, true>, 256, 0));
+        VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, wf_trace_kernel<COUNT, true>, kWfTraceThreads, 0));
         VT_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
         if (const char* e = getenv("VT_WF_SHADE_CTAS")) { const int v = atoi(e); if (v >= 1) per_sm_s = std::min(per_sm_s, v); }   // tuning knobs
         if (const char* e = getenv("VT_WF_TRACE_CTAS")) { const int v = atoi(e); if (v >= 1) per_sm_t = std::min(per_sm_t, v); }
@@ -781,18 +781,31 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
         c->wf_trace_blocks[ci] = std::max(1, per_sm_t) * std::max(1, sms);
         c->wf_sms = std::max(1, sms);
     }
+    // every trace warp can leave one partly filled chunk per queue behind (COUNT and plain builds may differ in occupancy)
+    c->wf_queue_slack = std::max(c->wf_queue_slack, (size_t)c->wf_trace_blocks[ci] * (kWfTraceThreads / 32) * kWfQueueChunk + 4096);
     const int n_items = my_tiles * kTile * kTile;
     // split the passes of this call into batches: at most wf_max_paths paths in flight over all lanes, and at least
     // `lanes` batches when there are enough passes, so that two batches always overlap
     const int lanes = std::max(1, std::min(c->wf_lanes, L.n_passes));
-    const int budget = (int)std::max<size_t>(1, c->wf_max_paths / (size_t)n_items / (size_t)lanes);
-    const int batch_max = std::max(1, std::min(budget, (L.n_passes + lanes - 1) / lanes));
-    const int n_iters = F.max_bounces + 2;
-    for (int k = 0; k < lanes; ++k) {
-        const int rc = wf_reserve(c, k, (size_t)n_items * (size_t)batch_max, n_iters);
-        if (rc != VT_OK) return rc;
+    // the pools never take more than half of the memory that is free right now (another context, torch or NCCL may share the GPU)
+    size_t budget_paths = c->wf_max_paths;
+    {
+        size_t free_b = 0, total_b = 0, held = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            for (int k = 0; k < vt_ctx::kWfLanes; ++k) held += c->wf_capacity[k] * kWfBytesPerPath;
+            budget_paths = std::min(budget_paths, std::max<size_t>((free_b + held) / 2 / kWfBytesPerPath, (size_t)n_items * lanes));
+        }
     }
-    const int classify_blocks = c->wf_sms * 8;
+    const int budget = (int)std::max<size_t>(1, budget_paths / (size_t)n_items / (size_t)lanes);
+    int batch_max = std::max(1, std::min(budget, (L.n_passes + lanes - 1) / lanes));
+    const int n_iters = F.max_bounces + 3;
+    for (;;) {                                        // a smaller batch gives the same bits: halve it when the allocation fails
+        int rc = VT_OK;
+        for (int k = 0; k < lanes && rc == VT_OK; ++k) rc = wf_reserve(c, k, (size_t)n_items * (size_t)batch_max, n_iters);
+        if (rc == VT_OK) break;
+        if (batch_max == 1) return rc;
+        batch_max = (batch_max + 1) / 2;
+    }
     VT_CUDA(c, cudaEventRecord(c->wf_fork, c->stream));
     for (int k = 0; k < lanes; ++k) VT_CUDA(c, cudaStreamWaitEvent(c->wf_stream[k], c->wf_fork, 0));
     int batch = 0;
@@ -802,21 +815,29 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
         WfState S = c->wf[lane]; S.n_items = n_items;
         WfCounts* cn = c->d_wf_counts[lane];
         const int nb = std::min(batch_max, L.n_passes - pass0);
+        const size_t vis_bytes = (((size_t)n_items * nb + 2047) / 2048) * 256;
         if (batch >= lanes) VT_CUDA(c, cudaStreamWaitEvent(st, c->wf_acc[lane], 0));      // the lane's samples were folded in
         VT_CUDA(c, cudaMemsetAsync(cn, 0, sizeof(WfCounts) * (size_t)n_iters, st));
         { WfTimer t(c, VT_K_GENERATE, st);
           const int gen_x = n_items / 256, gen_rows = std::min(nb, std::max(1, (c->wf_sms * 8 + gen_x - 1) / gen_x));   // enough CTAs for every SM, else 1 row
-          wf_generate_kernel<COUNT><<<dim3((unsigned)gen_x, (unsigned)gen_rows), 256, 0, st>>>(V, F, L, S, S.buf[0], pass0, nb, cn, prim, c->d_counters); }
+          wf_generate_kernel<COUNT><<<dim3((unsigned)gen_x, (unsigned)gen_rows), 256, 0, st>>>(V, F, L, S, pass0, nb, cn, prim, c->d_counters); }
         c->launches += 1;
         for (int it = 0; ; ++it) {
-            // it == 0: primary rays; it >= 1: the shadow + bounce rays emitted by wf_shade(it)
-            // generation `it` lives in buf[it & 1]; wf_shade compacts its survivors into buf[(it + 1) & 1]
-            const WfBuf& cur = S.buf[it & 1]; const WfBuf& nxt = S.buf[(it + 1) & 1];
-            { WfTimer t(c, VT_K_TRACE, st); if (V.dist != nullptr && !COUNT) wf_trace_kernel<COUNT, true><<<c->wf_trace_blocks[ci], 256, 0, st>>>(V, S, cur, cn + it, c->d_counters);
-              else wf_trace_kernel<COUNT, false><<<c->wf_trace_blocks[ci], 256, 0, st>>>(V, S, cur, cn + it, c->d_counters); }
-            { WfTimer t(c, VT_K_CLASSIFY, st); wf_classify_kernel<<<classify_blocks, 256, 0, st>>>(V, F, L, S, cur, pass0, cn + it, cn + it + 1, it == 0 ? prim : nullptr); }
-            { WfTimer t(c, VT_K_SHADE, st); wf_shade_launch(COUNT, (unsigned)c->wf_shade_blocks[ci], st, V, F, S, cur, nxt, cn + it + 1, c->d_counters); }
-            c->launches += 3;
+            // it == 0: primary rays; it >= 1: the shadow + bounce rays emitted by wf_shade(it - 1). Generation `it` of the paths
+            // lives in state[it & 1]; wf_shade compacts its survivors into state[(it + 1) & 1]. Counts block `it` holds the size
+            // of generation `it`, block it + 1 the shade queues wf_trace fills.
+            if (it > 0) { WfTimer t(c, VT_K_OTHER, st); VT_CUDA(c, cudaMemsetAsync(S.vis, 0, vis_bytes, st)); }
+            { WfTimer t(c, VT_K_TRACE, st);
+              if (V.dist != nullptr && !COUNT) wf_trace_kernel<COUNT, true><<<c->wf_trace_blocks[ci], kWfTraceThreads, 0, st>>>(V, F, S, it == 0 ? 1 : 0, cn + it, cn + it + 1, c->d_counters);
+              else wf_trace_kernel<COUNT, false><<<c->wf_trace_blocks[ci], kWfTraceThreads, 0, st>>>(V, F, S, it == 0 ? 1 : 0, cn + it, cn + it + 1, c->d_counters); }
+            c->launches += 1;
+            if (it == 0 && prim != nullptr && pass0 + nb == L.n_passes) {
+                WfTimer t(c, VT_K_OTHER, st);
+                wf_primary_kernel<<<dim3((unsigned)(c->wf_sms * 4), kWfQueues), 256, 0, st>>>(V, F, L, S, pass0, cn + 1, prim);
+                c->launches += 1;
+            }
+            { WfTimer t(c, VT_K_SHADE, st); wf_shade_launch(COUNT, (unsigned)c->wf_shade_blocks[ci], st, V, F, S, it & 1, cn + it + 1, c->d_counters); }
+            c->launches += 1;
             if (it == F.max_bounces) break;
         }
         // accumulation.fs in pass order: on the caller's stream, after this batch's last shade
@@ -853,29 +874,14 @@ int vt_render(vt_ctx* c, int first_sample, int n_passes)
         if (!c->dist_valid && skip_wanted(c) && c->variant == 2) { const int rc = rebuild_dist(c); if (rc != VT_OK) return rc; }
         const Volume V = make_volume(c); const Frame F = make_frame(c);
         int* prim = c->primary_enabled ? c->d_primary : nullptr;
-        if (c->variant == 2 && L.integrator == VT_INTEGRATOR_PATHTRACER) {
+        if (c->variant == 2 && L.integrator == VT_INTEGRATOR_PATHTRACER && c->st.max_bounces <= kWfMaxBounces) {
             const int rc = c->count_enabled ? wf_render<true>(c, V, F, L, my_tiles, prim) : wf_render<false>(c, V, F, L, my_tiles, prim);
             if (rc != VT_OK) return rc;
             c->launches -= 1;          // the common epilogue below counts one launch
-        } else if (c->variant != 1) {
+        } else {
             const dim3 grid((unsigned)(my_tiles * kCtasPerTile));
             if (c->count_enabled) vt_render_kernel<true><<<grid, 128, 0, c->stream>>>(V, F, L, c->d_accum, prim, c->d_counters);
             else vt_render_kernel<false><<<grid, 128, 0, c->stream>>>(V, F, L, c->d_accum, prim, c->d_counters);
-        } else {
-            // persistent: one wave of CTAs sized by occupancy, pixels handed out through a global work counter
-            const int ci = c->count_enabled ? 1 : 0;
-            if (c->ps_blocks[ci] == 0) {
-                int per_sm = 0, sms = 0;
-                if (ci) VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vt_render_ps_kernel<true>, 128, 0));
-                else VT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vt_render_ps_kernel<false>, 128, 0));
-                VT_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-                c->ps_blocks[ci] = std::max(1, per_sm) * std::max(1, sms);
-            }
-            const int n_items = my_tiles * kTile * kTile;
-            const int blocks = std::min(c->ps_blocks[ci], (n_items + 127) / 128);
-            VT_CUDA(c, cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), c->stream));
-            if (ci) vt_render_ps_kernel<true><<<blocks, 128, 0, c->stream>>>(V, F, L, n_items, c->d_accum, prim, c->d_counters, c->d_work);
-            else vt_render_ps_kernel<false><<<blocks, 128, 0, c->stream>>>(V, F, L, n_items, c->d_accum, prim, c->d_counters, c->d_work);
         }
         VT_CUDA(c, cudaGetLastError());
         c->launches += 1;

@@ -4,6 +4,7 @@
 // /root/reference/src/shaders). Arithmetic contract: vt_math.cuh.
 #pragma once
 #include "vt_math.cuh"
+#include "vt_mem.cuh"
 
 namespace vt {
 
@@ -108,7 +109,7 @@ VT_DEV f4 rng_next(const Frame& F, int2& off, Tally<COUNT>& tl)        // random
 {
     f4 r = mk4(0.f, 0.f, 0.f, 0.f);
     if (off.x >= 0 && off.y >= 0 && off.x < F.noise_w && off.y < F.noise_h) {
-        const float4 t = __ldg(F.noise + ((size_t)off.x + (size_t)off.y * (size_t)F.noise_w));
+        const float4 t = ldg_keep(F.noise + ((size_t)off.x + (size_t)off.y * (size_t)F.noise_w));
         r = mk4(t.x, t.y, t.z, t.w);
     }
     // (x + 1) % w and (y + 1) % h for 0 <= x < w, 0 <= y < h (rng_offset and this function keep them there)
@@ -550,10 +551,10 @@ VT_DEV f3 env_lookup(const Frame& F, f2 uv, Tally<COUNT>& tl)
     int x1 = x0 + 1, y1 = y0 + 1;
     x0 = max(0, min(x0, w - 1)); x1 = max(0, min(x1, w - 1));
     y0 = max(0, min(y0, h - 1)); y1 = max(0, min(y1, h - 1));
-    const float4 p00 = __ldg(F.env + ((size_t)x0 + (size_t)y0 * w));
-    const float4 p10 = __ldg(F.env + ((size_t)x1 + (size_t)y0 * w));
-    const float4 p01 = __ldg(F.env + ((size_t)x0 + (size_t)y1 * w));
-    const float4 p11 = __ldg(F.env + ((size_t)x1 + (size_t)y1 * w));
+    const float4 p00 = ldg_keep(F.env + ((size_t)x0 + (size_t)y0 * w));
+    const float4 p10 = ldg_keep(F.env + ((size_t)x1 + (size_t)y0 * w));
+    const float4 p01 = ldg_keep(F.env + ((size_t)x0 + (size_t)y1 * w));
+    const float4 p11 = ldg_keep(F.env + ((size_t)x1 + (size_t)y1 * w));
     const f3 top = mk3(gmix(p00.x, p10.x, a), gmix(p00.y, p10.y, a), gmix(p00.z, p10.z, a));
     const f3 bot = mk3(gmix(p01.x, p11.x, a), gmix(p01.y, p11.y, a), gmix(p01.z, p11.z, a));
     VT_TALLY(Q, 1);
@@ -581,14 +582,14 @@ VT_DEV float cdf_u_at(const Frame& F, int x, int y, Tally<COUNT>& tl)
 {
     VT_TALLY(E, 1);
     if ((unsigned)x >= (unsigned)F.cdf_u_w || (unsigned)y >= (unsigned)F.cdf_u_h) return 0.0f;
-    return __ldg(F.cdf_u + ((size_t)x + (size_t)y * F.cdf_u_w));
+    return ldg_keep(F.cdf_u + ((size_t)x + (size_t)y * F.cdf_u_w));
 }
 template <bool COUNT>
 VT_DEV float cdf_v_at(const Frame& F, int i, Tally<COUNT>& tl)
 {
     VT_TALLY(E, 1);
     if ((unsigned)i >= (unsigned)F.cdf_v_n) return 0.0f;
-    return __ldg(F.cdf_v + i);
+    return ldg_keep(F.cdf_v + i);
 }
 // The searches of envMapSample.h:70-123 return R(s) = max({0} U {m in [1, n-2] : cdf[m] <= s}) whenever the CDF is sorted
 // (the probe order is then irrelevant). The guide table stores R(j / K) for j = 0..K-1 and n-2 for j = K, so for
@@ -597,10 +598,10 @@ VT_DEV float cdf_v_at(const Frame& F, int i, Tally<COUNT>& tl)
 VT_DEV int cdf_search_guided(const float* __restrict__ cdf, const unsigned short* __restrict__ guide, int K, float s)
 {
     const int j = min(K - 1, f2i(s * (float)K));
-    int lo = (int)__ldg(guide + j), hi = (int)__ldg(guide + j + 1) + 1;
+    int lo = (int)ldg_keep(guide + j), hi = (int)ldg_keep(guide + j + 1) + 1;
     while (lo != hi - 1) {
         const int m = (lo + hi) >> 1;
-        if (s < __ldg(cdf + m)) hi = m; else lo = m;
+        if (s < ldg_keep(cdf + m)) hi = m; else lo = m;
     }
     return lo;
 }
@@ -705,7 +706,7 @@ VT_DEV f3 sample_microfacet(f3 refl, float e, f3 wo, float ux, float uy, f4& f_p
 VT_DEV float fetch_mat(const Frame& F, int i)                     // texelFetch(materialDataTexture); out of range -> 0
 {
     if ((unsigned)i >= (unsigned)F.n_materials) return 0.0f;
-    return __ldg(F.materials + i);
+    return ldg_keep(F.materials + i);
 }
 VT_DEV f3 mat_vec(const Frame& F, int off) { return mk3(fetch_mat(F, off), fetch_mat(F, off + 1), fetch_mat(F, off + 2)); }
 
@@ -779,7 +780,8 @@ VT_DEV LightSample sample_light(const Volume& V, const Frame& F, const Basis& hb
     const int num_lights = F.n_emissive + 1;                      // :78
     const int light_index = f2i(u.x * (float)num_lights);         // :79
     if (light_index < num_lights - 1) {                           // :81
-        const int eidx = __ldg(F.emissive + light_index);         // :85
+        // :85 texelFetch: an index outside the list (negative u.x: only from a caller-supplied noise table) reads 0
+        const int eidx = ((unsigned)light_index < (unsigned)F.n_emissive) ? __ldg(F.emissive + light_index) : 0;
         int ex, ey, ez;
         voxel_index_to_pos(eidx, V.X, V.Y, ex, ey, ez);           // :86
         ls.target = ex + ey * V.X + ez * V.X * V.Y;

@@ -12,11 +12,11 @@ cudaError_t wf_shade_blocks_per_sm(bool count, int* blocks)
                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, wf_shade_kernel<false>, VT_WF_SHADE_THREADS, 0);
 }
 
-void wf_shade_launch(bool count, unsigned int blocks, cudaStream_t st, const Volume& V, const Frame& F, const WfState& S, const WfBuf& in,
-                     const WfBuf& out, WfCounts* cnt, Counters* counters)
+void wf_shade_launch(bool count, unsigned int blocks, cudaStream_t st, const Volume& V, const Frame& F, const WfState& S, int gen,
+                     WfCounts* cnt, Counters* counters)
 {
-    if (count) wf_shade_kernel<true><<<blocks, VT_WF_SHADE_THREADS, 0, st>>>(V, F, S, in, out, cnt, counters);
-    else wf_shade_kernel<false><<<blocks, VT_WF_SHADE_THREADS, 0, st>>>(V, F, S, in, out, cnt, counters);
+    if (count) wf_shade_kernel<true><<<blocks, VT_WF_SHADE_THREADS, 0, st>>>(V, F, S, gen, cnt, counters);
+    else wf_shade_kernel<false><<<blocks, VT_WF_SHADE_THREADS, 0, st>>>(V, F, S, gen, cnt, counters);
 }
 
 } // namespace vt
