@@ -206,6 +206,53 @@ int vt_measure_l2_bandwidth(vt_ctx* ctx, size_t bytes, int reps, float* gb_per_s
 int vt_debug_advance(vt_ctx* ctx, const float* d, const float* e, const float* tau, const int32_t* nmax, size_t n,
                      float* d_out, int32_t* k_out, int literal);
 
+/* ---- render groups: one frame sharded over several GPUs (new-build surface; the reference renders on a single GL context,
+ * renderer/renderer.cpp:556-645). Paths are independent and the scene is replicated (every context of the group receives
+ * the same uploads through the vt_* calls above), so rendering needs no collective; the group owns the partition
+ * (vt_set_partition), the combination of the per-rank accumulators and the replication of edits.
+ *   VT_PART_TILES    64x64 tiles dealt round-robin; the root gathers W*H*16/world bytes per rank; bit-identical to one GPU.
+ *   VT_PART_SAMPLES  rank r renders sampleCount = p*world + r and keeps a float4 SUM; SUM-reduce to the root + one division
+ *                    (fp summation order differs from the running average: equal within 1e-5 relative).
+ * Exchange: NCCL bound at run time (ncclCommInitAll in one process, ncclCommInitRank across processes), or this library's own
+ * kernel over peer memory (one process only; the only choice when two contexts share a device). The exchange runs on side
+ * streams from a snapshot of the accumulators: rendering continues while it is in flight. */
+typedef struct vt_group vt_group;
+enum { VT_EXCHANGE_NCCL = 0, VT_EXCHANGE_PEER = 1 };
+/* one process: creates (and owns) one context per listed device / adopts existing contexts (rank = position) */
+int vt_group_create(int n, const int* devices, int mode, vt_group** out);
+int vt_group_adopt(int n, vt_ctx* const* contexts, int mode, vt_group** out);
+/* one process per GPU: rank 0 obtains the 128-byte NCCL id, the launcher hands it to every rank, every rank joins */
+int vt_group_unique_id(void* out128);
+int vt_group_join(vt_ctx* ctx, const void* id128, int rank, int world, int mode, vt_group** out);
+void vt_group_destroy(vt_group* group);
+const char* vt_group_last_error(const vt_group* group);
+int vt_group_size(const vt_group* group);                       /* world size */
+int vt_group_local_size(const vt_group* group);                 /* contexts held by this process */
+vt_ctx* vt_group_context(vt_group* group, int local_index);     /* for the scene / camera / settings uploads */
+int vt_group_rank(const vt_group* group, int local_index);
+int vt_group_set_exchange(vt_group* group, int exchange);
+int vt_group_get_exchange(const vt_group* group);
+int vt_nccl_version(void);                                      /* 0 when libnccl.so.2 could not be loaded */
+/* Renderer::render on every local context (each renders its share); asynchronous like vt_render */
+int vt_group_render(vt_group* group, int first_sample, int n_passes);
+int vt_group_reset_accumulation(vt_group* group);
+int vt_group_sync(vt_group* group);
+/* combination of the accumulators: begin returns at once (snapshot + exchange on side streams), end waits and, in the process
+ * that holds rank 0, copies the finished W*H RGBA float32 frame to rgba_out (may be NULL); read_average = begin + end */
+int vt_group_begin_combine(vt_group* group);
+int vt_group_end_combine(vt_group* group, float* rgba_out);
+int vt_group_read_average(vt_group* group, float* rgba_out);
+void* vt_group_result_device_ptr(vt_group* group);
+int vt_group_last_exchange_ms(vt_group* group, float* ms);      /* device time of the last exchange on the root's side stream */
+size_t vt_group_exchange_bytes(const vt_group* group);          /* bytes the root receives per combination */
+/* edits on every replica (renderer/actions.cpp:20-52; volume edits reset the accumulation) */
+int vt_group_pick(vt_group* group, float px, float py);
+int vt_group_pick_focal(vt_group* group, float px, float py);
+int vt_group_add_voxel(vt_group* group, float motion_x, float motion_y);
+int vt_group_remove_voxel(vt_group* group);
+/* up to 256 bytes from the process holding rank `root` to all ranks (the 32-byte action record of an edit issued on one rank) */
+int vt_group_broadcast(vt_group* group, void* host_buf, size_t bytes, int root);
+
 #ifdef __cplusplus
 }
 #endif

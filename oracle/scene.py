@@ -325,9 +325,8 @@ def env_function(rgb):
     m = max(w, h)
     if m > MAX_CDF_SIZE:
         nw = int(f32(w) / f32(m) * f32(MAX_CDF_SIZE)); nh = int(f32(h) / f32(m) * f32(MAX_CDF_SIZE))
-        fx, fy = w // nw, h // nh
-        assert fx * nw == w and fy * nh == h, "box downscale needs integer factors"
-        rgb = rgb.reshape(nh, fy, nw, fx, 3).astype(np.float64).mean(axis=(1, 3)).astype(np.float32)
+        assert nw > 0 and nh > 0, "image too elongated for the CDF size limit"
+        rgb = vto.resize_box(rgb, nw, nh)          # area-weighted box filter (integer factors: the plain box mean)
     lum = (rgb[..., 0] * f32(0.2126) + rgb[..., 1] * f32(0.7152)) + rgb[..., 2] * f32(0.0722)
     k1 = np.array([0.25, 0.5, 0.25], np.float32)
     p = np.pad(lum, 1, mode="edge")

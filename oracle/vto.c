@@ -20,6 +20,36 @@
 #include <omp.h>
 #endif
 
+/* image.cpp:309-321: reduction of the environment image before the CDFs are built. The reference calls OpenImageIO's resize
+ * (unpinned, absent here: SURVEY 8c); the contract of this build is an area-weighted box filter: output pixel (x, y) averages the
+ * source rectangle [x sx, (x+1) sx) x [y sy, (y+1) sy), edge pixels weighted by their overlap, double accumulator, rows outer. */
+void vto_resize_box(const float* rgb, int w, int h, int nw, int nh, float* out)
+{
+    const double sx = (double)w / (double)nw, sy = (double)h / (double)nh;
+    int x, y, c, i, j;
+    for (y = 0; y < nh; y++) {
+        const double y0 = (double)y * sy, y1 = (double)(y + 1) * sy;
+        int j0 = (int)floor(y0), j1 = (int)ceil(y1);
+        if (j1 > h) j1 = h;
+        for (x = 0; x < nw; x++) {
+            const double x0 = (double)x * sx, x1 = (double)(x + 1) * sx;
+            int i0 = (int)floor(x0), i1 = (int)ceil(x1);
+            if (i1 > w) i1 = w;
+            for (c = 0; c < 3; c++) {
+                double acc = 0.0;
+                for (j = j0; j < j1; j++) {
+                    const double wy = (y1 < (double)(j + 1) ? y1 : (double)(j + 1)) - (y0 > (double)j ? y0 : (double)j);
+                    for (i = i0; i < i1; i++) {
+                        const double wx = (x1 < (double)(i + 1) ? x1 : (double)(i + 1)) - (x0 > (double)i ? x0 : (double)i);
+                        acc += (wy * wx) * (double)rgb[((size_t)j * w + i) * 3 + c];
+                    }
+                }
+                out[((size_t)y * nw + x) * 3 + c] = (float)(acc / (sx * sy));
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* small helpers                                                              */
 /* ------------------------------------------------------------------------- */

@@ -123,6 +123,8 @@ uint32_t vto_hash(uint32_t seed);                                     /* random.
 void vto_rng_offset(int px, int py, int sequence, int rw, int rh, int out[2]); /* random.h:13-18 */
 int vto_dda_step_cap(int X, int Y, int Z);                            /* dda.h:98 */
 
+/* image.cpp:309-321 as this build defines it: area-weighted box reduction of an RGB float image to nw x nh */
+void vto_resize_box(const float* rgb, int w, int h, int nw, int nh, float* out);
 /* image.cpp:68-283,349-389 on an already filtered single-channel image */
 void vto_build_cdf(const float* lum, int w, int h, float* cdf_u /*(w+1)*h*/, float* cdf_v /*h+1*/,
                    float* integral);

@@ -78,6 +78,7 @@ def lib():
     L.vto_rng_offset.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.vto_dda_step_cap.argtypes = [C.c_int, C.c_int, C.c_int]
     L.vto_dda_step_cap.restype = C.c_int
+    L.vto_resize_box.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
     L.vto_build_cdf.argtypes = [f32p, C.c_int, C.c_int, f32p, f32p, f32p]
     for name in ("sin", "cos", "acos", "exp2", "log2"):
         fn = getattr(L, "vto_m_" + name)
@@ -263,6 +264,14 @@ def trace_rays(scene, rays):
     r = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
     out = np.empty((r.shape[0], 4), np.float32)
     lib().vto_trace_rays(C.byref(scene), _fp(r), r.shape[0], _fp(out))
+    return out
+
+
+def resize_box(rgb, nw, nh):
+    """Area-weighted box reduction of an (h, w, 3) float32 image (the contract that stands in for OIIO's resize)."""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    out = np.empty((nh, nw, 3), np.float32)
+    lib().vto_resize_box(_fp(rgb), rgb.shape[1], rgb.shape[0], int(nw), int(nh), _fp(out))
     return out
 
 

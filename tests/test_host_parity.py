@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import scene as oscene
+from oracle import vto
 from tests import util
 
 
@@ -86,7 +87,8 @@ def test_prune_interior_emissive_matches_oracle(host):
 
 def test_calculate_cdf_matches_oracle(host, tmp_path):
     from voxeltoy_b200 import scenes
-    for size in [(256, 128), (1024, 512), (64, 48)]:
+    # 1000x500, 1500x750 and 3200x1600 reduce by non-integer factors (area-weighted box filter)
+    for size in [(256, 128), (1024, 512), (64, 48), (1000, 500), (1500, 750), (3200, 1600), (700, 1100)]:
         rgb = scenes.synthetic_env(*size)
         got = host.calculate_cdf(rgb)
         ref = oscene.build_env(rgb)
@@ -94,6 +96,10 @@ def test_calculate_cdf_matches_oracle(host, tmp_path):
         assert np.array_equal(got["cdf_u"], ref["cdf_u"]) and np.array_equal(got["cdf_v"], ref["cdf_v"])
         assert got["integral"] == ref["integral"]
         assert np.all(np.diff(got["cdf_v"]) >= 0) and got["cdf_v"][-1] == 1.0
+    # integer factors: the general filter IS the plain box mean
+    rgb = scenes.synthetic_env(1024, 512)
+    small = vto.resize_box(rgb, 512, 256)
+    assert np.array_equal(small, rgb.reshape(256, 2, 512, 2, 3).astype(np.float64).mean(axis=(1, 3)).astype(np.float32))
 
 
 def test_image_file_readers(host, tmp_path):

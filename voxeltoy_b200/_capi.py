@@ -92,6 +92,34 @@ SIGNATURES = {
     "vt_device_count": (C.c_int, []),
     "vt_version": (C.c_char_p, []),
     "vt_debug_trace_rays": (C.c_int, [P, f32p, C.c_size_t, f32p]),
+    # render groups (multi-GPU): G = vt_group*
+    "vt_group_create": (C.c_int, [C.c_int, i32p, C.c_int, C.POINTER(C.c_void_p)]),
+    "vt_group_adopt": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
+    "vt_group_unique_id": (C.c_int, [C.c_void_p]),
+    "vt_group_join": (C.c_int, [P, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vt_group_destroy": (None, [C.c_void_p]),
+    "vt_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "vt_group_size": (C.c_int, [C.c_void_p]),
+    "vt_group_local_size": (C.c_int, [C.c_void_p]),
+    "vt_group_context": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "vt_group_rank": (C.c_int, [C.c_void_p, C.c_int]),
+    "vt_group_set_exchange": (C.c_int, [C.c_void_p, C.c_int]),
+    "vt_group_get_exchange": (C.c_int, [C.c_void_p]),
+    "vt_nccl_version": (C.c_int, []),
+    "vt_group_render": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vt_group_reset_accumulation": (C.c_int, [C.c_void_p]),
+    "vt_group_sync": (C.c_int, [C.c_void_p]),
+    "vt_group_begin_combine": (C.c_int, [C.c_void_p]),
+    "vt_group_end_combine": (C.c_int, [C.c_void_p, f32p]),
+    "vt_group_read_average": (C.c_int, [C.c_void_p, f32p]),
+    "vt_group_result_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "vt_group_last_exchange_ms": (C.c_int, [C.c_void_p, f32p]),
+    "vt_group_exchange_bytes": (C.c_size_t, [C.c_void_p]),
+    "vt_group_pick": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "vt_group_pick_focal": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "vt_group_add_voxel": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "vt_group_remove_voxel": (C.c_int, [C.c_void_p]),
+    "vt_group_broadcast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
 }
 
 _LIB = None

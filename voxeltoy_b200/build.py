@@ -48,6 +48,12 @@ def build(force=False, verbose=False):
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(ROOT, "include"), "-I", HERE,
                                                                             "-o", lib] + cus + cpps
         subprocess.check_call(cmd)
+    # the C++ multi-GPU demo (tools/vt_group_demo.cpp): a host program without Python over the same library
+    demo_src = os.path.join(ROOT, "tools", "vt_group_demo.cpp")
+    demo = os.path.join(HERE, "vt_group_demo")
+    if os.path.exists(demo_src) and (force or _newer(demo, [demo_src, lib])):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", "-o", demo, demo_src,
+                               "-L", HERE, "-lvoxeltoy_b200", "-Wl,-rpath,$ORIGIN"])
     return lib
 
 

@@ -21,18 +21,33 @@ VT_GLOBAL void vt_env_rgba_kernel(const float* __restrict__ rgb, float4* __restr
     if (i < n) out[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 1.0f);
 }
 
-// image.cpp:309-335: box filter by integer factors (double accumulator, rows then columns), Rec.709 luminance
-VT_GLOBAL void vt_env_luminance_kernel(const float* __restrict__ rgb, int w, int nw, int nh, int fx, int fy, float* __restrict__ lum)
+// image.cpp:309-335: reduction to <= 512 texels per side + Rec.709 luminance. The reduction is this build's area-weighted box
+// filter (host/image.cpp generateImageFunction: source rectangle [x sx, (x+1) sx) x [y sy, (y+1) sy), edge pixels weighted by
+// their overlap, double accumulator, rows outer); same operations in the same order as the host, so the same bits. With
+// integer factors every weight is exactly 1.
+VT_GLOBAL void vt_env_luminance_kernel(const float* __restrict__ rgb, int w, int h, int nw, int nh, float* __restrict__ lum)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= nw || y >= nh) return;
     float ch[3];
-    const double inv = (double)(fx * fy);
-    for (int c = 0; c < 3; ++c) {
-        double s = 0.0;
-        for (int j = 0; j < fy; ++j)
-            for (int i = 0; i < fx; ++i) s += (double)rgb[((size_t)(y * fy + j) * w + (x * fx + i)) * 3 + c];
-        ch[c] = (float)(s / inv);
+    if (nw == w && nh == h) {
+        for (int c = 0; c < 3; ++c) ch[c] = rgb[((size_t)y * w + x) * 3 + c];
+    } else {
+        const double sx = (double)w / (double)nw, sy = (double)h / (double)nh;
+        const double y0 = (double)y * sy, y1 = (double)(y + 1) * sy, x0 = (double)x * sx, x1 = (double)(x + 1) * sx;
+        const int j0 = (int)floor(y0), j1 = min(h, (int)ceil(y1)), i0 = (int)floor(x0), i1 = min(w, (int)ceil(x1));
+        const double area = sx * sy;
+        for (int c = 0; c < 3; ++c) {
+            double acc = 0.0;
+            for (int j = j0; j < j1; ++j) {
+                const double wy = fmin(y1, (double)(j + 1)) - fmax(y0, (double)j);
+                for (int i = i0; i < i1; ++i) {
+                    const double wx = fmin(x1, (double)(i + 1)) - fmax(x0, (double)i);
+                    acc += (wy * wx) * (double)rgb[((size_t)j * w + i) * 3 + c];
+                }
+            }
+            ch[c] = (float)(acc / area);
+        }
     }
     lum[(size_t)y * nw + x] = (ch[0] * 0.2126f + ch[1] * 0.7152f) + ch[2] * 0.0722f;
 }

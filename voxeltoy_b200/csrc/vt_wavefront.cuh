@@ -44,7 +44,7 @@ namespace vt {
 
 constexpr int kWfQueues = 5;          // 0 = finish, 1..3 = material type 0..2, 4 = other material types
 #ifndef VT_WF_LIVE_MIN
-#define VT_WF_LIVE_MIN 28
+#define VT_WF_LIVE_MIN 20
 #endif
 #ifndef VT_WF_SHADE_THREADS
 #define VT_WF_SHADE_THREADS 128      // threads per wf_shade CTA (64 / 128 / 256 measured in round 1: 84.2 / 84.2 / 84.6 ms per step)
@@ -52,12 +52,14 @@ constexpr int kWfQueues = 5;          // 0 = finish, 1..3 = material type 0..2, 
 #ifndef VT_WF_SHADE_MIN_BLOCKS
 #define VT_WF_SHADE_MIN_BLOCKS (1024 / VT_WF_SHADE_THREADS)
 #endif
-constexpr int kWfLiveMin = VT_WF_LIVE_MIN;        // refill the warp when fewer lanes than this hold a ray
+// wf_trace steps its rays in chunks of kWfStepChunk DDA iterations and keeps stepping, chunk after chunk, while at least
+// kWfLiveMin lanes still run a ray; only then does it pay for a retire + refill round (about as many instructions as a
+// chunk). Round 1 retired and refilled after every 16-iteration chunk: half the lanes had finished by then (rays average
+// 17 iterations on C2) and 21 of 32 lanes did work.
+constexpr int kWfLiveMin = VT_WF_LIVE_MIN;
 #ifndef VT_WF_STEP_CHUNK
 #define VT_WF_STEP_CHUNK 16
 #endif
-// DDA iterations between two refill checks (round 1, C2 trace ms per 256-spp step: 6 / 8 / 10 / 12 / 14 / 16 / 20 / 24
-// iterations -> 88.3 / 84.4 / 82.5 / 81.2 / 82.1 / 81.0 / 84.0 / 84.6; C3 and C4 also prefer 16)
 constexpr int kWfStepChunk = VT_WF_STEP_CHUNK;
 #ifndef VT_WF_GRAB
 #define VT_WF_GRAB 128
@@ -69,6 +71,7 @@ constexpr int kWfGrab = VT_WF_GRAB;                       // rays a warp reserve
 constexpr int kWfSkipMinLanes = VT_WF_SKIP_MIN_LANES;     // lanes that must want an empty-space skip (or half of the running ones) before the warp pays for one
 constexpr int kWfQueueChunk = 64;                         // shade-queue entries a trace warp reserves per atomic
 constexpr int kWfTraceThreads = 256;
+constexpr unsigned int kWfPark = 64;                      // ring entries per trace warp (a power of two >= 2 * 32 - 1)
 constexpr unsigned int kWfInvalid = 0xffffffffu;          // slot word of an unused queue entry
 constexpr int kWfMaxBounces = 511;                        // the bounce count travels in 9 bits of the ray record
 
@@ -95,9 +98,10 @@ struct WfState {
     //   b: dis xyz, 1/d x      c: 1/d y z          (the DDA state after dda.h:16-34; the step direction is the sign of 1/d)
     // status = DDA_RUNNING for a ray to be traced; a ray that dda_begin already resolved (start voxel outside the grid or NaN)
     // carries its final status and position: wf_trace routes it without stepping, so every queue append happens in one place.
-    int4* __restrict__ rq_a[2];
-    float4* __restrict__ rq_b[2];
-    float2* __restrict__ rq_c[2];
+    int4* __restrict__ rq_a;                  // 2 * rq_cap records each: region r starts at r * rq_cap
+    float4* __restrict__ rq_b;
+    float2* __restrict__ rq_c;
+    unsigned int rq_cap;
     unsigned int* __restrict__ vis;           // shadow-ray results of the generation being traced: bit slot & 31 of word slot >> 5, 1 = light visible (zeroed before every trace)
     // shade queues: (slot, hit ix | iy << 16, hit iz | flags << 16, path id) + the rng word (rng linear offset | pending NaN mask << 29)
     int4* __restrict__ sq[kWfQueues];
@@ -173,9 +177,10 @@ VT_DEV int4 wf_entry(unsigned int slot, const Dda& s, int flags, unsigned int pi
 
 VT_DEV void wf_store_ray(const WfState& S, int region, unsigned int slot, int status, const Dda& s, int kind, int bounces, int aux, int rngw)
 {
-    st_stream16(S.rq_a[region] + slot, make_int4(wf_pack16(s.ix, s.iy), (s.iz & 0xffff) | (kind << 16) | (status << 18) | (s.nanmask << 20) | (bounces << 23), aux, rngw));
-    st_stream16(S.rq_b[region] + slot, make_float4(s.dx, s.dy, s.dz, s.sx < 0 ? -s.ex : s.ex));     // |1/d| > 0 (dda_begin): the sign bit is free
-    st_stream8(S.rq_c[region] + slot, make_float2(s.sy < 0 ? -s.ey : s.ey, s.sz < 0 ? -s.ez : s.ez));
+    const size_t at = (size_t)slot + (region ? (size_t)S.rq_cap : 0);
+    st_stream16(S.rq_a + at, make_int4(wf_pack16(s.ix, s.iy), (s.iz & 0xffff) | (kind << 16) | (status << 18) | (s.nanmask << 20) | (bounces << 23), aux, rngw));
+    st_stream16(S.rq_b + at, make_float4(s.dx, s.dy, s.dz, s.sx < 0 ? -s.ex : s.ex));     // |1/d| > 0 (dda_begin): the sign bit is free
+    st_stream8(S.rq_c + at, make_float2(s.sy < 0 ? -s.ey : s.ey, s.sz < 0 ? -s.ez : s.ez));
 }
 
 // Slot reservation in the next generation, aggregated lanes -> warp (ballot) -> CTA (shared-memory atomic) -> one global
@@ -291,8 +296,12 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
 
 // ---------------------------------------------------------------------------------------------------------
 // wf_trace: the loop of dda.h:38-57 for the ray records of one generation, then the routing of the finished path.
-// Persistent warps; a warp reserves kWfGrab rays per atomic and its lanes refill from that range whenever fewer than
-// kWfLiveMin of them hold a ray. Ray index w in [0, 2n): w < n = shadow ray of slot w, else bounce ray of slot w - n.
+// Persistent warps; a warp reserves kWfGrab rays per atomic (a static round-robin deal of the blocks was 20 % slower: every
+// launch then waits for its unluckiest warp) and its lanes refill from that range whenever fewer than kWfLiveMin of them
+// still run a ray. Ray index w in [0, 2n): w < n = shadow ray of slot w, else bounce / primary ray of slot w - n.
+// Finished bounce / primary rays are not routed by the few lanes that happen to retire in a round: they park (slot, hit
+// voxel, status) in a per-warp shared-memory ring, and whenever 32 are parked the whole warp routes and appends them at
+// full width (wf_trace_flush).
 // ---------------------------------------------------------------------------------------------------------
 #ifndef VT_WF_TRACE_MIN_BLOCKS
 #define VT_WF_TRACE_MIN_BLOCKS 6
@@ -304,6 +313,10 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S, const int primar
 {
     // per-warp cursors into the shade queues: [next, end) of the chunk the warp is filling (warp-uniform, touched by lane 0)
     __shared__ unsigned int cur_next[kWfTraceThreads / 32][kWfQueues], cur_end[kWfTraceThreads / 32][kWfQueues];
+    // per-warp ring of finished bounce / primary rays waiting to be routed: slot, hit x | y << 16, hit z | status << 16
+    __shared__ unsigned int park_slot[kWfTraceThreads / 32][kWfPark];
+    __shared__ int park_xy[kWfTraceThreads / 32][kWfPark], park_zs[kWfTraceThreads / 32][kWfPark];
+    unsigned int park_head = 0, park_cnt = 0;       // warp-uniform
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -320,16 +333,65 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S, const int primar
     bool have = false, exhausted = false;
     unsigned int range_next = 0, range_end = 0;     // warp-uniform
     unsigned int w = 0;                             // ray index of the lane's ray
-    int status = DDA_NOHIT, chunks = 0;
+    int status = DDA_NOHIT, guard = 0;
     const int chunk_guard = (V.X + V.Y + V.Z) / kWfStepChunk + 8;   // belt and braces: see dda_begin on why rays always leave
     Dda s;
     s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.steps = 0; s.bkey = -1; s.brick = 0ull;
     s.dx = s.dy = s.dz = 0.f; s.ex = s.ey = s.ez = 0.f; s.sx = s.sy = s.sz = 1;
 
+    // routes up to 32 parked paths at full width: looks at the ray record again (kind, bounce count, path id, rng word), finds
+    // the queue (pathTracer.fs:202-208, :214, :282-291) and appends the entries; slots are reserved per warp in chunks
+    auto route_parked = [&]() {
+        const unsigned nf = min(park_cnt, 32u);
+        int q = -1, rngw = 0;
+        int4 entry = make_int4(0, 0, 0, 0);
+        if ((unsigned)lane < nf) {
+            const unsigned at = (park_head + (unsigned)lane) & (kWfPark - 1);
+            const unsigned slot = park_slot[warp][at];
+            const int xy = park_xy[warp][at], zs = park_zs[warp][at];
+            const int4 a = S.rq_a[(size_t)slot + (size_t)S.rq_cap];   // kind, NaN mask, bounce count, path id, rng word
+            const int st = zs >> 16, hy = wf_hi16(xy), nanmask = (a.y >> 20) & 7;
+            const int kind = (a.y >> 16) & 3, bounces = (int)((unsigned)a.y >> 23);
+            const bool ground = (st != DDA_HIT) && !(nanmask & 2) && (hy < 0);                     // dda.h:75-78
+            const int flags = (st == DDA_HIT ? WF_HIT_VOXEL : (ground ? WF_HIT_GROUND : 0)) | (nanmask << WF_HIT_NAN_SHIFT)
+                              | (kind == WF_RAY_PRIMARY ? WF_HIT_PRIMARY : 0) | (bounces << WF_HIT_BOUNCE_SHIFT);
+            q = wf_route(V, F, flags, kind == WF_RAY_PRIMARY ? -1 : bounces, wf_lo16(xy), hy, wf_lo16(zs));
+            entry = make_int4((int)slot, xy, (zs & 0xffff) | (flags << 16), a.z);
+            rngw = a.w;
+        }
+        park_head = (park_head + nf) & (kWfPark - 1); park_cnt -= nf;
+        // routed paths -> shade queues, slots reserved per warp in chunks
+        unsigned pending = __ballot_sync(full, q >= 0);
+        while (pending != 0u) {                                     // one round per queue present: usually one or two
+            const int k = __shfl_sync(full, q, __ffs(pending) - 1);
+            const unsigned m = __ballot_sync(full, q == k);
+            pending &= ~m;
+            const unsigned cnt_k = (unsigned)__popc(m);
+            const unsigned nx = cur_next[warp][k], avail = cur_end[warp][k] - nx;
+            unsigned base2 = 0;
+            if (avail < cnt_k) {                                    // the old chunk is filled up first, the rest opens a new one
+                if (lane == 0) base2 = atomicAdd(&cnext->sq[k], (unsigned)kWfQueueChunk);
+                base2 = __shfl_sync(full, base2, 0);
+            }
+            if (q == k) {
+                const unsigned rank = (unsigned)__popc(m & lt);
+                const unsigned dst = rank < avail ? nx + rank : base2 + (rank - avail);
+                st_stream16(S.sq[k] + dst, entry); st_stream4(S.sq_rng[k] + dst, rngw);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (avail < cnt_k) { cur_next[warp][k] = base2 + (cnt_k - avail); cur_end[warp][k] = base2 + (unsigned)kWfQueueChunk; }
+                else cur_next[warp][k] = nx + cnt_k;
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    };
+
     for (;;) {
         // ---- refill idle lanes ---------------------------------------------------------------------------
         const unsigned need = __ballot_sync(full, !have);
-        if (!exhausted && __popc(need) > 32 - kWfLiveMin) {
+        if (!exhausted && need != 0u) {
             if (range_next >= range_end) {
                 unsigned base = 0;
                 if (lane == 0) base = atomicAdd(&cnt->work, (unsigned)kWfGrab);
@@ -341,16 +403,15 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S, const int primar
             if (!have) {
                 const unsigned r = range_next + (unsigned)__popc(need & lt);
                 if (r < range_end) {
-                    const int region = r >= n ? 1 : 0;
-                    const unsigned slot = r - (region ? n : 0u);
-                    const int4 a = S.rq_a[region][slot];                 // re-read at retire: default caching
-                    const float4 b = ld_stream16(S.rq_b[region] + slot); const float2 c = ld_stream8(S.rq_c[region] + slot);
+                    const size_t at = r < n ? (size_t)r : (size_t)(r - n) + (size_t)S.rq_cap;
+                    const int4 a = S.rq_a[at];                           // re-read at retire: default caching
+                    const float4 b = ld_stream16(S.rq_b + at); const float2 c = ld_stream8(S.rq_c + at);
                     s.ix = wf_lo16(a.x); s.iy = wf_hi16(a.x); s.iz = wf_lo16(a.y);
                     s.dx = b.x; s.dy = b.y; s.dz = b.z; s.ex = gabs(b.w); s.ey = gabs(c.x); s.ez = gabs(c.y);
                     s.sx = f2bits(b.w) < 0 ? -1 : 1; s.sy = f2bits(c.x) < 0 ? -1 : 1; s.sz = f2bits(c.y) < 0 ? -1 : 1;
                     s.steps = 0; s.bkey = -1;
                     status = (a.y >> 18) & 3;                            // DDA_RUNNING, or the final status dda_begin found
-                    chunks = 0;
+                    guard = chunk_guard;
                     w = r;
                     have = true;
                 }
@@ -359,79 +420,70 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S, const int primar
         }
         if (__ballot_sync(full, have) == 0u) { if (exhausted) break; else continue; }
         // ---- the hot loop ----------------------------------------------------------------------------------
-        if (have && status == DDA_RUNNING) {       // lanes leave the chunk through `break`: one reconvergence point per chunk, not per step
-            #pragma unroll
-            for (int k = 0; k < kWfStepChunk; ++k) {
-                status = dda_step<COUNT>(V, s, tl);
-                if (status != DDA_RUNNING) break;
+        for (;;) {
+            if (have && status == DDA_RUNNING) {   // lanes leave the chunk through `break`: one reconvergence point per chunk, not per step
+                #pragma unroll
+                for (int k = 0; k < kWfStepChunk; ++k) {
+                    status = dda_step<COUNT>(V, s, tl);
+                    if (status != DDA_RUNNING) break;
+                }
+                if (--guard < 0 && status == DDA_RUNNING) status = DDA_NOHIT;
             }
-        }
-        if (++chunks > chunk_guard && status == DDA_RUNNING) status = DDA_NOHIT;
-        if (SKIP && !COUNT) {                     // counting builds step every voxel so that S stays the algorithmic count
-            // the cheap part (one byte per lane) runs converged; the skip itself only when enough lanes want it, so that its
-            // divergent set-up is not paid for one or two lanes while the rest of the warp idles
-            const bool running = have && status == DDA_RUNNING;
-            const int radius = running ? dda_skip_radius(V, s) : 0;
-            const unsigned m_run = __ballot_sync(full, running), m_want = __ballot_sync(full, radius >= 2);
-            if (m_want != 0u && (__popc(m_want) >= kWfSkipMinLanes || 2 * __popc(m_want) >= __popc(m_run))) {
-                if (radius >= 2) {
-                    const int skipped = dda_skip(V, s, radius);
+            if (SKIP && !COUNT) {                 // counting builds step every voxel so that S stays the algorithmic count
+                // the cheap part (one byte per lane) runs converged; the skip itself only when enough lanes want it, so that its
+                // divergent set-up is not paid for one or two lanes while the rest of the warp idles
+                const bool running = have && status == DDA_RUNNING;
+                const int radius = running ? dda_skip_radius(V, s) : 0;
+                const unsigned m_running = __ballot_sync(full, running), m_want = __ballot_sync(full, radius >= 2);
+                if (m_want != 0u && (__popc(m_want) >= kWfSkipMinLanes || 2 * __popc(m_want) >= __popc(m_running))) {
+                    if (radius >= 2) {
+                        const int skipped = dda_skip(V, s, radius);
 #ifdef VT_SKIP_STATS
-                    dbg_calls += 1; dbg_ok += skipped > 0; dbg_steps += skipped;
+                        dbg_calls += 1; dbg_ok += skipped > 0; dbg_steps += skipped;
 #else
-                    (void)skipped;
+                        (void)skipped;
 #endif
+                    }
                 }
             }
+            // keep stepping while enough lanes still run a ray; once all rays are handed out (no refill can follow), until none does
+            const unsigned m_run = __ballot_sync(full, have && status == DDA_RUNNING);
+            if (exhausted ? (m_run == 0u) : (__popc(m_run) < kWfLiveMin)) break;
         }
         // ---- retire finished rays --------------------------------------------------------------------------
-        int q = -1, rngw = 0;
-        int4 entry = make_int4(0, 0, 0, 0);
+        bool park = false;
+        unsigned int p_slot = 0; int p_xy = 0, p_zs = 0;
         if (have && status != DDA_RUNNING) {
-            const int region = w >= n ? 1 : 0;
-            const unsigned slot = w - (region ? n : 0u);
-            const int4 a = S.rq_a[region][slot];                        // kind, bounce count, light target / path id, rng word
-            const int kind = (a.y >> 16) & 3;
-            s.nanmask = (a.y >> 20) & 7;                                // only a ray resolved by dda_begin can carry NaN components
-            if (kind == WF_RAY_SHADOW) {
-                if (wf_light_visible(V, a.z, status, s)) atomicOr(vis + (slot >> 5), 1u << (slot & 31));
-            } else {
-                const int bounces = (int)((unsigned)a.y >> 23);
-                const int flags = wf_hit_flags(status, s) | (kind == WF_RAY_PRIMARY ? WF_HIT_PRIMARY : 0) | (bounces << WF_HIT_BOUNCE_SHIFT);
-                q = wf_route(V, F, flags, kind == WF_RAY_PRIMARY ? -1 : bounces, s.ix, s.iy, s.iz);
-                entry = wf_entry(slot, s, flags, (unsigned)a.z);
-                rngw = a.w;
+            if (w < n) {                               // shadow ray of slot w
+                if (F.n_emissive == 0) {
+                    // towards the environment (the only light there is): visible iff nothing was hit, the virtual ground included
+                    // (a NaN height is stored as 0, so the ground test needs no NaN mask). No second look at the record.
+                    if (status != DDA_HIT && !(s.iy < 0)) atomicOr(vis + (w >> 5), 1u << (w & 31));
+                } else {
+                    const int4 a = S.rq_a[w];                           // light target; NaN mask of a ray resolved by dda_begin
+                    s.nanmask = (a.y >> 20) & 7;
+                    if (wf_light_visible(V, a.z, status, s)) atomicOr(vis + (w >> 5), 1u << (w & 31));
+                    s.nanmask = 0;
+                }
+            } else {                                   // bounce / primary ray: parked, routed later at full width
+                park = true;
+                p_slot = w - n; p_xy = wf_pack16(s.ix, s.iy); p_zs = (s.iz & 0xffff) | (status << 16);
             }
-            s.nanmask = 0;
             have = false;
         }
-        // routed paths -> shade queues, slots reserved per warp in chunks (converged)
-        if (__ballot_sync(full, q >= 0) != 0u) {
-            #pragma unroll
-            for (int k = 0; k < kWfQueues; ++k) {
-                const unsigned m = __ballot_sync(full, q == k);
-                if (m == 0u) continue;
-                const unsigned cnt_k = (unsigned)__popc(m);
-                const unsigned nx = cur_next[warp][k], avail = cur_end[warp][k] - nx;
-                unsigned base2 = 0;
-                if (avail < cnt_k) {                                    // the old chunk is filled up first, the rest opens a new one
-                    if (lane == 0) base2 = atomicAdd(&cnext->sq[k], (unsigned)kWfQueueChunk);
-                    base2 = __shfl_sync(full, base2, 0);
-                }
-                if (q == k) {
-                    const unsigned rank = (unsigned)__popc(m & lt);
-                    const unsigned dst = rank < avail ? nx + rank : base2 + (rank - avail);
-                    st_stream16(S.sq[k] + dst, entry); st_stream4(S.sq_rng[k] + dst, rngw);
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    if (avail < cnt_k) { cur_next[warp][k] = base2 + (cnt_k - avail); cur_end[warp][k] = base2 + (unsigned)kWfQueueChunk; }
-                    else cur_next[warp][k] = nx + cnt_k;
-                }
-                __syncwarp();
+        const unsigned m_park = __ballot_sync(full, park);
+        if (m_park != 0u) {
+            if (park) {
+                const unsigned at = (park_head + park_cnt + (unsigned)__popc(m_park & lt)) & (kWfPark - 1);
+                park_slot[warp][at] = p_slot; park_xy[warp][at] = p_xy; park_zs[warp][at] = p_zs;
             }
+            park_cnt += (unsigned)__popc(m_park);
+            __syncwarp();
         }
+        // ---- route 32 parked paths: every lane takes one (and once more after the loop for what is left) -------
+        if (park_cnt >= 32u) route_parked();
     }
+    if (park_cnt != 0u) route_parked();
     // the unused tail of the warp's chunks: marked invalid (wf_shade skips such entries)
     #pragma unroll
     for (int k = 0; k < kWfQueues; ++k)

@@ -163,17 +163,33 @@ static bool generateImageFunction(const float* rgbPixels, unsigned int imageWidt
     unsigned int w = imageWidth, h = imageHeight;
     const unsigned int m = std::max(w, h);
     if (m > MAX_CDF_SIZE) {                                                    // :309-321
+        // The reference resizes with OpenImageIO's default filter (ImageBufAlgo::resize), which no test pins and which is not
+        // available here. This build defines the reduction as an AREA-WEIGHTED BOX filter: output pixel (x, y)
+        // averages the source rectangle [x sx, (x+1) sx) x [y sy, (y+1) sy), sx = w / nw, sy = h / nh, edge pixels weighted by
+        // their overlap; double accumulator, rows outer. Integer factors give weights of exactly 1 (the plain box mean).
         const unsigned int nw = (unsigned int)((float)w / m * MAX_CDF_SIZE);
         const unsigned int nh = (unsigned int)((float)h / m * MAX_CDF_SIZE);
         if (nw == 0 || nh == 0) return false;
-        const unsigned int fx = w / nw, fy = h / nh;
-        if (fx * nw != w || fy * nh != h) return false;                        // box filter needs integer factors
+        const double sx = (double)w / (double)nw, sy = (double)h / (double)nh;
         std::vector<float> small((size_t)nw * nh * 3);
-        for (unsigned int y = 0; y < nh; ++y) for (unsigned int x = 0; x < nw; ++x) for (int c = 0; c < 3; ++c) {
-            double s = 0;
-            for (unsigned int j = 0; j < fy; ++j) for (unsigned int i = 0; i < fx; ++i)
-                s += src[((size_t)(y * fy + j) * w + (x * fx + i)) * 3 + c];
-            small[((size_t)y * nw + x) * 3 + c] = (float)(s / (double)(fx * fy));
+        for (unsigned int y = 0; y < nh; ++y) {
+            const double y0 = (double)y * sy, y1 = (double)(y + 1) * sy;
+            const unsigned int j0 = (unsigned int)std::floor(y0), j1 = std::min(h, (unsigned int)std::ceil(y1));
+            for (unsigned int x = 0; x < nw; ++x) {
+                const double x0 = (double)x * sx, x1 = (double)(x + 1) * sx;
+                const unsigned int i0 = (unsigned int)std::floor(x0), i1 = std::min(w, (unsigned int)std::ceil(x1));
+                for (int c = 0; c < 3; ++c) {
+                    double acc = 0;
+                    for (unsigned int j = j0; j < j1; ++j) {
+                        const double wy = std::min(y1, (double)(j + 1)) - std::max(y0, (double)j);
+                        for (unsigned int i = i0; i < i1; ++i) {
+                            const double wx = std::min(x1, (double)(i + 1)) - std::max(x0, (double)i);
+                            acc += (wy * wx) * (double)src[((size_t)j * w + i) * 3 + c];
+                        }
+                    }
+                    small[((size_t)y * nw + x) * 3 + c] = (float)(acc / (sx * sy));
+                }
+            }
         }
         src.swap(small); w = nw; h = nh;
     }

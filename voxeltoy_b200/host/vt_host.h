@@ -364,6 +364,41 @@ private:
     vtm::M44f m_mvm, m_invMvm, m_pm, m_invPm;
 };
 
+// ---- RendererGroup: one frame on several GPUs (new-build; the reference's Renderer owns a single GL context) ----------------
+// N replicas of the scene, one Renderer (and one vt_ctx) per CUDA device, behind the calls the UI makes on one Renderer:
+// scene / settings / camera changes and edit actions go to every replica, renderPasses() renders every replica's share of the
+// frame (64x64 tiles round-robin) or of the samples (sampleCount = p * N + rank), readAverage() combines the accumulators on
+// rank 0 through the C ABI's vt_group (NCCL over NVLink, or the library's peer-memory kernel). Single host thread, like the
+// reference's GL thread: every call only enqueues work on the replicas' streams.
+class RendererGroup {
+public:
+    enum Mode { MODE_TILES = VT_PART_TILES, MODE_SAMPLES = VT_PART_SAMPLES };
+    RendererGroup();
+    ~RendererGroup();
+    bool initialize(const std::vector<int>& cudaDevices, Mode mode);
+    size_t size() const { return m_renderers.size(); }
+    Renderer& renderer(size_t rank) { return *m_renderers[rank]; }
+    template <class F> void forEach(F f) { for (size_t i = 0; i < m_renderers.size(); ++i) f(*m_renderers[i]); }   // any Renderer call, on every replica
+    void resizeFrame(int width, int height);
+    void loadVoxFile(const std::string& file);
+    void loadMeshAtResolution(const std::string& file, int resolution);
+    void setVoxelData(const vtm::V3i& resolution, const std::vector<int32_t>& voxelMaterials, const std::vector<float>& materialData,
+                      const std::vector<int32_t>& emissiveVoxelIndices);
+    void updateRenderSettings(const RenderSettings& settings);
+    void requestAction(float x, float y, float dx, float dy, Action::PICKING_ACTION action, bool restartAccumulation);   // actions.cpp:5-18, on every replica
+    void resetRender();
+    void renderPasses(int nPasses);
+    bool beginCombine();                       // asynchronous: rendering may continue while the exchange is in flight
+    bool endCombine(float* rgbaOut);           // W*H RGBA float32, GL orientation
+    bool readAverage(float* rgbaOut) { return beginCombine() && endCombine(rgbaOut); }
+    vt_group* group() const { return m_group; }
+    const std::string& getStatus() const { return m_status; }
+private:
+    std::vector<Renderer*> m_renderers;
+    vt_group* m_group;
+    std::string m_status;
+};
+
 // ---- tools/tool.h:5-13, toolAddRemoveVoxel, toolFocalDistance -------------------------------------------------------------
 struct MouseEvent { int x, y; int buttons; int modifiers; };      // stands in for QMouseEvent
 struct KeyEvent { int key; };
