@@ -240,6 +240,7 @@ int vt_group_sync(vt_group* group);
 /* combination of the accumulators: begin returns at once (snapshot + exchange on side streams), end waits and, in the process
  * that holds rank 0, copies the finished W*H RGBA float32 frame to rgba_out (may be NULL); read_average = begin + end */
 int vt_group_begin_combine(vt_group* group);
+int vt_group_wait_combine(vt_group* group);                     /* stream-level: the contexts' streams wait for the exchange, the host does not */
 int vt_group_end_combine(vt_group* group, float* rgba_out);
 int vt_group_read_average(vt_group* group, float* rgba_out);
 void* vt_group_result_device_ptr(vt_group* group);

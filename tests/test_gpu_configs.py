@@ -199,23 +199,5 @@ def test_full_size_properties_c3(vt_ctx):
     vt_ctx.volume_upload(np.full(16 ** 3, -1, np.int32), (16, 16, 16))
 
 
-def _dense_noise_offsets_torch(n, offsets, density=0.35, seed=1, n_materials=8, chunk=64):
-    """scenes.dense_noise_grid + ids_to_offsets with torch on the GPU (test plumbing: the numpy generator needs 40 s at 1024^3);
-    same integers, checked against the numpy version below."""
-    import torch
-    dev = torch.device("cuda:0")
-    M = 0xFFFFFFFF
-    out = torch.empty((n, n, n), dtype=torch.int32)
-    x = torch.arange(n, dtype=torch.int64, device=dev)[None, None, :]
-    y = torch.arange(n, dtype=torch.int64, device=dev)[None, :, None]
-    offs = torch.as_tensor(np.asarray(offsets, np.int64), device=dev)
-    thr = int(density * 2 ** 32)
-    for z0 in range(0, n, chunk):
-        z = torch.arange(z0, min(n, z0 + chunk), dtype=torch.int64, device=dev)[:, None, None]
-        v = (x + y * n + z * (n * n) + seed * 0x9E3779B9) & M
-        v = (v * 747796405 + 2891336453) & M                                   # scenes.pcg_hash
-        w = ((torch.bitwise_right_shift(v, (v >> 28) + 4) ^ v) * 277803737) & M
-        h = ((w >> 22) ^ w) & M
-        ids = (h >> 8) & (n_materials - 1)
-        out[z0:z0 + chunk] = torch.where(h < thr, offs[ids], torch.full_like(ids, -1)).to(torch.int32).cpu()
-    return out.reshape(-1).numpy()
+def _dense_noise_offsets_torch(n, offsets, **kw):
+    return scenes.dense_noise_offsets_torch(n, offsets, **kw)

@@ -118,7 +118,7 @@ def test_group_two_contexts_on_one_gpu_peer_exchange():
 def test_group_nccl_in_process():
     if vt.load().vt_device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    assert vt.load().vt_nccl_version() > 0
+    assert G.DeviceGroup._lib().vt_nccl_version() > 0
     _check_group([0, 1])                      # NCCL by default on distinct devices
     _check_group([0, 1], exchange=G.DeviceGroup.EXCHANGE_PEER)
 

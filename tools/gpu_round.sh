@@ -5,7 +5,7 @@ TAG=${1:-run}; STEPS=${2:-6}
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.used --format=csv > $OUT/${TAG}_smi.txt 2>&1
 timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vs_reference.py tests/test_gpu_edges.py tests/test_gpu_renderer.py \
-    tests/test_gpu_env.py tests/test_gpu_headless.py tests/test_gpu_configs.py tests/test_gpu_fullsize.py -q -x --timeout 600 > $OUT/${TAG}_tests.log 2>&1
+    tests/test_gpu_env.py tests/test_gpu_group.py tests/test_gpu_headless.py tests/test_gpu_configs.py tests/test_gpu_fullsize.py -q -x --timeout 600 > $OUT/${TAG}_tests.log 2>&1
 echo "pytest rc=$?" >> $OUT/${TAG}_tests.log
 tail -5 $OUT/${TAG}_tests.log
 timeout 600 python bench.py --steps $STEPS --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err

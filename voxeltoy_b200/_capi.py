@@ -110,6 +110,7 @@ SIGNATURES = {
     "vt_group_reset_accumulation": (C.c_int, [C.c_void_p]),
     "vt_group_sync": (C.c_int, [C.c_void_p]),
     "vt_group_begin_combine": (C.c_int, [C.c_void_p]),
+    "vt_group_wait_combine": (C.c_int, [C.c_void_p]),
     "vt_group_end_combine": (C.c_int, [C.c_void_p, f32p]),
     "vt_group_read_average": (C.c_int, [C.c_void_p, f32p]),
     "vt_group_result_device_ptr": (C.c_void_p, [C.c_void_p]),

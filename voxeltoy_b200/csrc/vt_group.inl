@@ -44,8 +44,11 @@ NcclApi& nccl_api()
     static bool tried = false;
     if (tried) return api;
     tried = true;
+    // a copy that is already in the process (PyTorch's, when running under Python) wins; VT_NCCL_LIBRARY names one explicitly
+    if (const char* e = getenv("VT_NCCL_LIBRARY")) api.handle = dlopen(e, RTLD_NOW | RTLD_LOCAL);
     const char* names[] = { "libnccl.so.2", "libnccl.so" };
-    for (const char* nm : names) { api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+    for (const char* nm : names) { if (!api.handle) api.handle = dlopen(nm, RTLD_NOW | RTLD_NOLOAD); }
+    for (const char* nm : names) { if (!api.handle) api.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL); }
     if (!api.handle) return api;
 #define VT_NCCL_SYM(field, sym) api.field = (decltype(api.field))dlsym(api.handle, #sym)
     VT_NCCL_SYM(GetUniqueId, ncclGetUniqueId); VT_NCCL_SYM(CommInitRank, ncclCommInitRank); VT_NCCL_SYM(CommInitAll, ncclCommInitAll);
@@ -477,6 +480,20 @@ int vt_group_begin_combine(vt_group* g)
     if (rl >= 0) { VTG_CUDA(g, cudaSetDevice(g->ctx[rl]->device)); VTG_CUDA(g, cudaEventRecord(g->t1, g->side[rl])); }
     for (size_t i = 0; i < g->ctx.size(); ++i) { VTG_CUDA(g, cudaSetDevice(g->ctx[i]->device)); VTG_CUDA(g, cudaEventRecord(g->ev_done[i], g->side[i])); }
     g->pending = true;
+    return VT_OK;
+}
+
+// Orders every local context's stream after the exchange in flight (no host wait): work enqueued afterwards -- and CUDA events
+// recorded on those streams -- come after the combination. For device-side timing and for callers that consume
+// vt_group_result_device_ptr on the context's stream.
+int vt_group_wait_combine(vt_group* g)
+{
+    if (!g) return VT_ERR_INVALID;
+    if (!g->pending) return VT_OK;
+    for (size_t i = 0; i < g->ctx.size(); ++i) {
+        VTG_CUDA(g, cudaSetDevice(g->ctx[i]->device));
+        VTG_CUDA(g, cudaStreamWaitEvent(g->ctx[i]->stream, g->ev_done[i], 0));
+    }
     return VT_OK;
 }
 

@@ -13,6 +13,8 @@ plumbing around it and uses torch.distributed for the transport (NCCL over NVLin
            SUM-reduce followed by one division by the total pass count on the destination rank (fp-sum order differs
            from the reference's running average: equal within 1e-5 relative).
 """
+import os
+
 import numpy as np
 
 PART_NONE, PART_TILES, PART_SAMPLES = 0, 1, 2
@@ -110,9 +112,30 @@ class DeviceGroup:
     def __init__(self, handle, lib, contexts):
         self.h, self.lib, self.contexts = handle, lib, contexts
 
-    @staticmethod
-    def _lib():
+    _nccl_preloaded = False
+
+    @classmethod
+    def _lib(cls):
+        """The library binds NCCL at run time by soname (dlopen("libnccl.so.2")). In a Python process the copy that must win is
+        the one PyTorch ships (a later `import torch` would otherwise be handed the older system library under the same
+        soname), so it is loaded first when it exists."""
         from . import _capi
+        if not cls._nccl_preloaded:
+            cls._nccl_preloaded = True
+            import ctypes
+            import glob
+            import site
+            import sys
+            if "torch" not in sys.modules:
+                roots = list(site.getsitepackages()) + [p for p in sys.path if p.endswith("site-packages")]
+                for root in roots:
+                    hits = glob.glob(os.path.join(root, "nvidia", "nccl", "lib", "libnccl.so.2"))
+                    if hits:
+                        try:
+                            ctypes.CDLL(hits[0], mode=ctypes.RTLD_GLOBAL)
+                        except OSError:
+                            pass
+                        break
         return _capi.load()
 
     @classmethod
@@ -179,6 +202,13 @@ class DeviceGroup:
 
     def begin_combine(self):
         self._ck(self.lib.vt_group_begin_combine(self.h))
+
+    def wait_combine(self):
+        """Stream-level wait: the contexts' streams continue after the exchange (no host synchronisation)."""
+        self._ck(self.lib.vt_group_wait_combine(self.h))
+
+    def result_device_ptr(self):
+        return self.lib.vt_group_result_device_ptr(self.h)
 
     def end_combine(self, out=None, want=True):
         """Waits for the exchange. In the process that holds rank 0 returns the frame ((H, W, 4) float32; `out`: a host array

@@ -115,6 +115,44 @@ def dense_noise_grid(n, density=0.35, seed=1, n_materials=8, chunk=64):
     return out.reshape(-1)
 
 
+def dense_noise_offsets_torch(n, offsets, density=0.35, seed=1, n_materials=8, chunk=64, device="cuda"):
+    """dense_noise_grid + ids_to_offsets evaluated with torch on the GPU (the numpy generator needs 40 s at 1024^3); the same
+    integers (checked against the numpy version by tests/test_gpu_fullsize.py). Returns the int32 R32I grid on the host."""
+    import torch
+    dev = torch.device(device)
+    M = 0xFFFFFFFF
+    out = torch.empty((n, n, n), dtype=torch.int32)
+    x = torch.arange(n, dtype=torch.int64, device=dev)[None, None, :]
+    y = torch.arange(n, dtype=torch.int64, device=dev)[None, :, None]
+    offs = torch.as_tensor(np.asarray(offsets, np.int64), device=dev)
+    thr = int(density * 2 ** 32)
+    for z0 in range(0, n, chunk):
+        z = torch.arange(z0, min(n, z0 + chunk), dtype=torch.int64, device=dev)[:, None, None]
+        v = (x + y * n + z * (n * n) + seed * 0x9E3779B9) & M
+        v = (v * 747796405 + 2891336453) & M                                   # pcg_hash
+        w = ((torch.bitwise_right_shift(v, (v >> 28) + 4) ^ v) * 277803737) & M
+        h = ((w >> 22) ^ w) & M
+        ids = (h >> 8) & (n_materials - 1)
+        out[z0:z0 + chunk] = torch.where(h < thr, offs[ids], torch.full_like(ids, -1)).to(torch.int32).cpu()
+    return out.reshape(-1).numpy()
+
+
+def c4_scene(n=256):
+    """BASELINE config 4: procedural terrain, rock / metal band / emissive lava. dict(res, grid, materials, emissive_all)."""
+    ids = terrain_grid(n)
+    t = MaterialTable()
+    t.lambert((0.55, 0.5, 0.45)); t.metal((0.8, 0.8, 0.85), 60.0); t.lambert((0.3, 0.1, 0.05), emission=(6.0, 2.0, 0.5))
+    grid = ids_to_offsets(ids, t.offsets); mats = t.array()
+    return dict(res=(n, n, n), grid=grid, materials=mats, emissive_all=emissive_list(grid, mats))
+
+
+def c5_material_table():
+    t = MaterialTable()
+    for k in range(8):
+        (t.metal((0.9, 0.6 + 0.04 * k, 0.3), 30.0 + 20 * k) if k % 3 == 2 else t.lambert((0.3 + 0.08 * k, 0.5, 0.9 - 0.08 * k)))
+    return t
+
+
 def _value_noise2(x, z, seed):
     """Smooth deterministic 2-D value noise in [-1, 1] (bicubic-smoothstep interpolation of lattice hashes)."""
     xi, zi = np.floor(x).astype(np.int64), np.floor(z).astype(np.int64)
