@@ -185,6 +185,9 @@ int vt_voxelize(vt_ctx* ctx, const float* xyz, size_t n_verts, const uint32_t* i
 int vt_volume_assign_materials(vt_ctx* ctx, const int32_t* offsets_table, int n_table, int rule);
 /* elapsed GPU milliseconds of the last vt_voxelize (clear + scatter + derive), cudaEvent-timed */
 int vt_get_last_voxelize_ms(vt_ctx* ctx, float* ms);
+/* the same call's device time including what the pipeline needs next: the material-id grid made valid (cleared to "empty", the
+ * solid voxels filled) and the renderer's empty-space distance field */
+int vt_get_last_voxelize_full_ms(vt_ctx* ctx, float* ms);
 
 /* ---- services: renderer/services/*.cpp (1-vertex "compute" draws, service.cpp:10-20) ---- */
 int vt_pick(vt_ctx* ctx, float px, float py);                /* RendererServiceSelectActiveVoxel -> selectVoxel.vs */

@@ -85,6 +85,7 @@ SIGNATURES = {
     "vt_voxelize": (C.c_int, [P, f32p, C.c_size_t, u32p, C.c_size_t, f32p, C.c_int, C.c_int, C.c_int, C.c_int32]),
     "vt_volume_assign_materials": (C.c_int, [P, i32p, C.c_int, C.c_int]),
     "vt_get_last_voxelize_ms": (C.c_int, [P, f32p]),
+    "vt_get_last_voxelize_full_ms": (C.c_int, [P, f32p]),
     "vt_pick": (C.c_int, [P, C.c_float, C.c_float]),
     "vt_pick_focal": (C.c_int, [P, C.c_float, C.c_float]),
     "vt_add_voxel": (C.c_int, [P, C.c_float, C.c_float]),
@@ -400,6 +401,12 @@ class Context:
     def last_voxelize_ms(self):
         ms = C.c_float()
         self._ck(self.lib.vt_get_last_voxelize_ms(self.h, C.cast(C.byref(ms), f32p)))
+        return float(ms.value)
+
+    def last_voxelize_full_ms(self):
+        """Device time of the last vt_voxelize including the id grid and the distance field (scatter only: last_voxelize_ms)."""
+        ms = C.c_float()
+        self._ck(self.lib.vt_get_last_voxelize_full_ms(self.h, C.byref(ms)))
         return float(ms.value)
 
     def assign_materials(self, table, rule=1):

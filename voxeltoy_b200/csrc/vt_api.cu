@@ -10,10 +10,27 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace vt;
+
+// splits [0, n) over the host's threads
+template <class F> static void parallel_ranges(size_t n, F f)
+{
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = std::max(1u, std::min(nt, 32u));
+    if (n < ((size_t)1 << 22)) nt = 1;
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const size_t a = std::min(n, (size_t)t * per), b = std::min(n, a + per);
+        if (t + 1 == nt) f(t, a, b); else th.emplace_back(f, t, a, b);
+    }
+    for (auto& x : th) x.join();
+}
 
 extern "C" {
 
@@ -66,7 +83,7 @@ int vt_create(int device, vt_ctx** out)
         cudaMalloc(&c->d_counters, sizeof(Counters)) != cudaSuccess ||
         cudaMemcpy(c->d_shared, &sh, sizeof sh, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemset(c->d_counters, 0, sizeof(Counters)) != cudaSuccess ||
-        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess || cudaEventCreate(&c->ev2) != cudaSuccess) {
         vt_destroy(c); return VT_ERR_CUDA;
     }
     // defaults of the Renderer constructor (renderer.cpp:41-65) + pathTracer.fs:25-26,40-41
@@ -86,7 +103,7 @@ void vt_destroy(vt_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_bricks_empty); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]); cudaFree(c->d_materials); cudaFree(c->d_emissive);
+    cudaFree(c->d_ids); cudaFree(c->d_id_offset); cudaFree(c->d_bricks_alloc); cudaFree(c->d_bricks_empty); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]); cudaFree(c->d_materials); cudaFree(c->d_emissive);
     cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum); cudaFree(c->d_display);
     cudaFree(c->d_guide_v); cudaFree(c->d_guide_u);
     for (int k = 0; k < vt_ctx::kWfLanes; ++k) {
@@ -101,6 +118,8 @@ void vt_destroy(vt_ctx* c)
     cudaFree(c->d_primary); cudaFree(c->d_shared); cudaFree(c->d_result); cudaFree(c->d_counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    cudaFree(c->d_mesh_xyz); cudaFree(c->d_mesh_idx); cudaFree(c->d_mesh_M);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -124,29 +143,64 @@ static void volume_bounds(vt_ctx* c)
     }
 }
 
+static constexpr int kMaxIds = 65535;
+
+// (re)allocates the id grid for `id_bytes` per voxel
+static int alloc_ids(vt_ctx* c, int id_bytes)
+{
+    const size_t need = (size_t)c->X * c->Y * c->Z * (size_t)id_bytes;
+    if (need > c->ids_capacity || !c->d_ids) {
+        cudaFree(c->d_ids); c->d_ids = nullptr; c->ids_capacity = 0;
+        VT_CUDA(c, cudaMalloc(&c->d_ids, need));
+        c->ids_capacity = need;
+    }
+    c->id_bytes = id_bytes;
+    if (!c->d_id_offset) VT_CUDA(c, cudaMalloc(&c->d_id_offset, sizeof(int32_t) * (kMaxIds + 1)));
+    return VT_OK;
+}
+// installs the table id -> offset (host mirror + device copy); guarantees an id for offset 0
+static int set_id_table(vt_ctx* c, std::vector<int32_t> table)
+{
+    int zero = -1;
+    for (size_t i = 0; i < table.size(); ++i) if (table[i] == 0) { zero = (int)i; break; }
+    if (zero < 0) { zero = (int)table.size(); table.push_back(0); }
+    if ((int)table.size() > kMaxIds) return fail(c, VT_ERR_INVALID, "more than %d distinct material offsets in the volume", kMaxIds - 1);
+    if (!c->d_id_offset) VT_CUDA(c, cudaMalloc(&c->d_id_offset, sizeof(int32_t) * (kMaxIds + 1)));
+    c->h_id_offset = table; c->zero_id = zero;
+    VT_CUDA(c, cudaMemcpyAsync(c->d_id_offset, c->h_id_offset.data(), sizeof(int32_t) * table.size(), cudaMemcpyHostToDevice, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));       // h_id_offset may be replaced before the copy would otherwise run
+    return VT_OK;
+}
+
 static int alloc_volume(vt_ctx* c, int X, int Y, int Z)
 {
     VT_REQ(c, X > 0 && Y > 0 && Z > 0 && X <= 2048 && Y <= 2048 && Z <= 2048, "volume resolution must be in [1, 2048]^3");
-    if (X != c->X || Y != c->Y || Z != c->Z || !c->d_mat) {
-        cudaFree(c->d_mat); cudaFree(c->d_bricks_alloc); cudaFree(c->d_bricks_empty); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]);
-        c->d_mat = nullptr; c->d_bricks = nullptr; c->d_bricks_alloc = nullptr; c->d_bricks_empty = nullptr; c->d_dist[0] = c->d_dist[1] = nullptr; c->dist_valid = false;
-        c->X = X; c->Y = Y; c->Z = Z;
-        c->BX = (X + 3) / 4; c->BY = (Y + 3) / 4; c->BZ = (Z + 3) / 4;
-        c->PBX = c->BX + 2; c->PBY = c->BY + 2; c->PBZ = c->BZ + 2;
-        VT_CUDA(c, cudaMalloc(&c->d_mat, sizeof(int32_t) * (size_t)X * Y * Z));
-        VT_CUDA(c, cudaMalloc(&c->d_bricks_alloc, sizeof(unsigned long long) * (size_t)c->PBX * c->PBY * c->PBZ));
-        c->d_bricks = c->d_bricks_alloc + (1 + (size_t)c->PBX + (size_t)c->PBX * c->PBY);
-        {   // the empty template: zero inside the volume, the sentinel shell set (see dda_step); built once per resolution
-            const size_t npb = (size_t)c->PBX * c->PBY * c->PBZ;
-            VT_CUDA(c, cudaMalloc(&c->d_bricks_empty, npb * 8));
-            VT_CUDA(c, cudaMemsetAsync(c->d_bricks_empty, 0, npb * 8, c->stream));
-            vt_sentinel_kernel<<<grid_for(npb, 256), 256, 0, c->stream>>>(c->d_bricks_empty, X, Y, Z, c->PBX, c->PBY, c->PBZ);
-            c->launches += 1;
-            VT_CUDA(c, cudaGetLastError());
+    if (X != c->X || Y != c->Y || Z != c->Z || !c->d_bricks_alloc) {
+        // allocate into locals first: the context changes only when every allocation has succeeded
+        const int BX = (X + 3) / 4, BY = (Y + 3) / 4, BZ = (Z + 3) / 4, PBX = BX + 2, PBY = BY + 2, PBZ = BZ + 2;
+        const int CX = (X + 7) / 8, CY = (Y + 7) / 8, CZ = (Z + 7) / 8;
+        const size_t npb = (size_t)PBX * PBY * PBZ, nc = (size_t)CX * CY * CZ;
+        unsigned long long *bricks = nullptr, *empty = nullptr; unsigned char *d0 = nullptr, *d1 = nullptr;
+        cudaError_t e = cudaMalloc(&bricks, npb * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&empty, npb * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&d0, nc);
+        if (e == cudaSuccess) e = cudaMalloc(&d1, nc);
+        if (e != cudaSuccess) {
+            cudaFree(bricks); cudaFree(empty); cudaFree(d0); cudaFree(d1); cudaGetLastError();
+            return fail(c, VT_ERR_CUDA, "volume %dx%dx%d: %s", X, Y, Z, cudaGetErrorString(e));
         }
-        c->CX = (X + 7) / 8; c->CY = (Y + 7) / 8; c->CZ = (Z + 7) / 8;
-        VT_CUDA(c, cudaMalloc(&c->d_dist[0], (size_t)c->CX * c->CY * c->CZ));
-        VT_CUDA(c, cudaMalloc(&c->d_dist[1], (size_t)c->CX * c->CY * c->CZ));
+        VT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_ids); cudaFree(c->d_bricks_alloc); cudaFree(c->d_bricks_empty); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]);
+        c->d_ids = nullptr; c->ids_capacity = 0;
+        c->d_bricks_alloc = bricks; c->d_bricks_empty = empty; c->d_dist[0] = d0; c->d_dist[1] = d1; c->dist_valid = false;
+        c->X = X; c->Y = Y; c->Z = Z;
+        c->BX = BX; c->BY = BY; c->BZ = BZ; c->PBX = PBX; c->PBY = PBY; c->PBZ = PBZ; c->CX = CX; c->CY = CY; c->CZ = CZ;
+        c->d_bricks = c->d_bricks_alloc + (1 + (size_t)PBX + (size_t)PBX * PBY);
+        // the empty template: zero inside the volume, the sentinel shell set (see dda_step); built once per resolution
+        VT_CUDA(c, cudaMemsetAsync(c->d_bricks_empty, 0, npb * 8, c->stream));
+        vt_sentinel_kernel<<<grid_for(npb, 256), 256, 0, c->stream>>>(c->d_bricks_empty, X, Y, Z, PBX, PBY, PBZ);
+        c->launches += 1;
+        VT_CUDA(c, cudaGetLastError());
     }
     volume_bounds(c);
     return VT_OK;
@@ -178,29 +232,19 @@ static int rebuild_dist(vt_ctx* c)
     return VT_OK;
 }
 
-static int mat_normalize(vt_ctx* c)
-{
-    if (!c->mat_stale_empties) return VT_OK;
-    vt_clear_empty_offsets_kernel<<<grid_for((size_t)c->BX * c->Y * c->Z, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_mat, c->X, c->Y, c->Z, c->BX, c->PBX, c->PBX * c->PBY);
-    c->launches += 1;
-    VT_CUDA(c, cudaGetLastError());
-    c->mat_stale_empties = false;
-    return VT_OK;
-}
-
 static int rebuild_occupancy(vt_ctx* c)
 {
-    c->mat_stale_empties = false;                      // the caller has just written the whole grid
     int rc = clear_occupancy(c);
     if (rc != VT_OK) return rc;
     const size_t rows = (size_t)c->BX * c->Y * c->Z;
-    vt_build_bricks_kernel<<<grid_for(rows, 256), 256, 0, c->stream>>>(c->d_mat, c->d_bricks, c->X, c->Y, c->Z, c->BX, c->PBX, c->PBX * c->PBY);
+    vt_build_bricks_kernel<<<grid_for(rows, 256), 256, 0, c->stream>>>(c->d_ids, c->id_bytes, c->d_bricks, c->X, c->Y, c->Z, c->BX, c->PBX, c->PBX * c->PBY);
     c->launches += 1;
     c->dist_valid = false;                             // the renderer's distance field is rebuilt on its next use
     VT_CUDA(c, cudaGetLastError());
     return VT_OK;
 }
 
+// R32I offsets (renderer.cpp:863-872: x fastest, -1 empty) -> id table + id grid on the device
 int vt_volume_upload(vt_ctx* c, const int32_t* mat, int X, int Y, int Z)
 {
     if (!c) return VT_ERR_INVALID;
@@ -208,8 +252,50 @@ int vt_volume_upload(vt_ctx* c, const int32_t* mat, int X, int Y, int Z)
     int rc = alloc_volume(c, X, Y, Z);
     if (rc != VT_OK) return rc;
     const size_t n = (size_t)X * Y * Z;
-    if (mat) VT_CUDA(c, cudaMemcpyAsync(c->d_mat, mat, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    else VT_CUDA(c, cudaMemsetAsync(c->d_mat, 0xff, n * sizeof(int32_t), c->stream));
+    if (!mat) {
+        rc = alloc_ids(c, 1); if (rc != VT_OK) return rc;
+        rc = set_id_table(c, std::vector<int32_t>()); if (rc != VT_OK) return rc;
+        VT_CUDA(c, cudaMemsetAsync(c->d_ids, 0xff, n, c->stream));
+    } else {
+        // pass 1: the distinct offsets (every negative value means empty)
+        std::vector<std::vector<int32_t>> found(64);
+        parallel_ranges(n, [&](unsigned t, size_t a, size_t b) {
+            std::vector<int32_t>& v = found[t];
+            int32_t last = -1;
+            for (size_t i = a; i < b; ++i) {
+                const int32_t o = mat[i];
+                if (o < 0 || o == last) continue;
+                last = o;
+                if (std::find(v.begin(), v.end(), o) == v.end()) { v.push_back(o); if (v.size() > (size_t)kMaxIds) return; }
+            }
+        });
+        std::vector<int32_t> table;
+        for (auto& v : found) table.insert(table.end(), v.begin(), v.end());
+        std::sort(table.begin(), table.end());
+        table.erase(std::unique(table.begin(), table.end()), table.end());
+        const size_t n_sorted = table.size();
+        rc = set_id_table(c, table); if (rc != VT_OK) return rc;
+        const int id_bytes = c->h_id_offset.size() <= 255 ? 1 : 2;
+        rc = alloc_ids(c, id_bytes); if (rc != VT_OK) return rc;
+        // pass 2: offsets -> ids (binary search in the sorted part of the table; a one-entry cache catches the runs)
+        const std::vector<int32_t>& T = c->h_id_offset;
+        std::vector<unsigned char> ids(n * (size_t)id_bytes);
+        parallel_ranges(n, [&](unsigned, size_t a, size_t b) {
+            int32_t last = -1; int last_id = -1;
+            for (size_t i = a; i < b; ++i) {
+                const int32_t o = mat[i];
+                int id = -1;
+                if (o >= 0) {
+                    if (o == last) id = last_id;
+                    else { id = (int)(std::lower_bound(T.begin(), T.begin() + n_sorted, o) - T.begin()); last = o; last_id = id; }
+                }
+                if (id_bytes == 1) ids[i] = (unsigned char)(id < 0 ? 0xff : id);
+                else reinterpret_cast<uint16_t*>(ids.data())[i] = (uint16_t)(id < 0 ? 0xffff : id);
+            }
+        });
+        VT_CUDA(c, cudaMemcpyAsync(c->d_ids, ids.data(), ids.size(), cudaMemcpyHostToDevice, c->stream));
+        VT_CUDA(c, cudaStreamSynchronize(c->stream));   // `ids` goes out of scope
+    }
     rc = rebuild_occupancy(c);
     if (rc != VT_OK) return rc;
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -250,19 +336,27 @@ int vt_emissive_upload(vt_ctx* c, const int32_t* idx, size_t n)
     if (!c) return VT_ERR_INVALID;
     VT_REQ(c, idx || n == 0, "null emissive list");
     VT_BIND(c);
-    if (n > 0) { const int rc = mat_normalize(c); if (rc != VT_OK) return rc; }   // the list may name voxels that are empty
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
     c->n_emissive = n;
     return upload_array(c, (void**)&c->d_emissive, idx, n * sizeof(int32_t));
 }
 
-int vt_read_volume(vt_ctx* c, int32_t* out)
+int vt_read_volume(vt_ctx* c, int32_t* out)            // the R32I view of the id grid (renderer.cpp:863-872)
 {
     if (!c || !out) return VT_ERR_INVALID;
     VT_BIND(c);
-    { const int rc = mat_normalize(c); if (rc != VT_OK) return rc; }
-    VT_CUDA(c, cudaMemcpyAsync(out, c->d_mat, sizeof(int32_t) * (size_t)c->X * c->Y * c->Z, cudaMemcpyDeviceToHost, c->stream));
+    const size_t n = (size_t)c->X * c->Y * c->Z;
+    std::vector<unsigned char> ids(n * (size_t)c->id_bytes);
+    VT_CUDA(c, cudaMemcpyAsync(ids.data(), c->d_ids, ids.size(), cudaMemcpyDeviceToHost, c->stream));
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    const std::vector<int32_t>& T = c->h_id_offset;
+    const int id_bytes = c->id_bytes;
+    parallel_ranges(n, [&](unsigned, size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) {
+            if (id_bytes == 1) { const unsigned v = ids[i]; out[i] = (v == 0xffu || v >= T.size()) ? -1 : T[v]; }
+            else { const unsigned v = reinterpret_cast<const uint16_t*>(ids.data())[i]; out[i] = (v == 0xffffu || v >= T.size()) ? -1 : T[v]; }
+        }
+    });
     return VT_OK;
 }
 
@@ -517,7 +611,8 @@ static bool skip_wanted(const vt_ctx* c)
 static Volume make_volume(const vt_ctx* c)
 {
     Volume V;
-    V.mat = c->d_mat; V.bricks = c->d_bricks;
+    V.ids8 = c->id_bytes == 1 ? (const uint8_t*)c->d_ids : nullptr; V.ids16 = c->id_bytes == 2 ? (const uint16_t*)c->d_ids : nullptr;
+    V.id_offset = c->d_id_offset; V.bricks = c->d_bricks;
     V.X = c->X; V.Y = c->Y; V.Z = c->Z;
     V.BX = c->PBX; V.BXY = c->PBX * c->PBY;               // strides of the padded brick array
     const bool skip = c->dist_valid && skip_wanted(c);
@@ -867,6 +962,24 @@ int vt_reset_counters(vt_ctx* c)
 }
 
 // ---- voxelizer ----------------------------------------------------------------------------------------
+// mesh staging buffers of vt_voxelize, kept between calls (a 512^3 voxelization takes ~0.1 ms on the device: three cudaMalloc /
+// cudaFree pairs per call would cost more than the kernels)
+static int mesh_reserve(vt_ctx* c, size_t n_verts, size_t n_indices)
+{
+    if (n_verts > c->mesh_verts_cap || !c->d_mesh_xyz) {
+        cudaFree(c->d_mesh_xyz); c->d_mesh_xyz = nullptr; c->mesh_verts_cap = 0;
+        VT_CUDA(c, cudaMalloc(&c->d_mesh_xyz, std::max<size_t>(1, n_verts) * 3 * sizeof(float)));
+        c->mesh_verts_cap = n_verts;
+    }
+    if (n_indices > c->mesh_idx_cap || !c->d_mesh_idx) {
+        cudaFree(c->d_mesh_idx); c->d_mesh_idx = nullptr; c->mesh_idx_cap = 0;
+        VT_CUDA(c, cudaMalloc(&c->d_mesh_idx, std::max<size_t>(1, n_indices) * sizeof(unsigned int)));
+        c->mesh_idx_cap = n_indices;
+    }
+    if (!c->d_mesh_M) VT_CUDA(c, cudaMalloc(&c->d_mesh_M, 16 * sizeof(float)));
+    return VT_OK;
+}
+
 int vt_voxelize(vt_ctx* c, const float* xyz, size_t n_verts, const uint32_t* indices, size_t n_indices,
                 const float M[16], int X, int Y, int Z, int32_t fill)
 {
@@ -876,55 +989,67 @@ int vt_voxelize(vt_ctx* c, const float* xyz, size_t n_verts, const uint32_t* ind
     for (size_t i = 0; i < n_indices; ++i) VT_REQ(c, indices[i] < n_verts, "vertex index out of range");
     VT_BIND(c);
     int rc = alloc_volume(c, X, Y, Z);
+    if (rc == VT_OK) rc = alloc_ids(c, 1);
+    if (rc == VT_OK) rc = set_id_table(c, std::vector<int32_t>(1, fill));     // id 0 = the fill record (+ an id for offset 0, see set_id_table)
+    if (rc == VT_OK) rc = mesh_reserve(c, n_verts, n_indices);
     if (rc != VT_OK) return rc;
-    float* d_xyz = nullptr; unsigned int* d_idx = nullptr; float* d_M = nullptr;
-    VT_CUDA(c, cudaMalloc(&d_xyz, std::max<size_t>(1, n_verts) * 3 * sizeof(float)));
-    VT_CUDA(c, cudaMalloc(&d_idx, std::max<size_t>(1, n_indices) * sizeof(unsigned int)));
-    VT_CUDA(c, cudaMalloc(&d_M, 16 * sizeof(float)));
-    VT_CUDA(c, cudaMemcpyAsync(d_xyz, xyz, n_verts * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    VT_CUDA(c, cudaMemcpyAsync(d_idx, indices, n_indices * sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));
-    VT_CUDA(c, cudaMemcpyAsync(d_M, M, 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    VT_CUDA(c, cudaMemcpyAsync(c->d_mesh_xyz, xyz, n_verts * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    VT_CUDA(c, cudaMemcpyAsync(c->d_mesh_idx, indices, n_indices * sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));
+    VT_CUDA(c, cudaMemcpyAsync(c->d_mesh_M, M, 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     const int n_tris = (int)(n_indices / 3);
-    // timed region: clear + scatter + derive (kernel time incl. grid clear, excl. OBJ parse and H2D)
+    const size_t n = (size_t)X * Y * Z;
+    // timed region A (ev0..ev1), SURVEY 8d "kernel time incl. grid clear, excl. OBJ parse and H2D": clear of the bit grid + scatter.
+    // timed region B (ev0..ev2): + the id grid made valid (cleared to empty, solid voxels filled) + the renderer's distance field.
     VT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     rc = clear_occupancy(c);
     if (rc != VT_OK) return rc;
     if (n_tris > 0) {
         const int ctas = std::max(1, std::min((n_tris + 3) / 4, 148 * 16));
-        vt_voxelize_kernel<<<ctas, 128, 0, c->stream>>>(d_xyz, d_idx, n_tris, d_M, X, Y, Z, c->PBX, c->PBX * c->PBY, c->d_bricks);
+        vt_voxelize_kernel<<<ctas, 128, 0, c->stream>>>(c->d_mesh_xyz, c->d_mesh_idx, n_tris, c->d_mesh_M, X, Y, Z, c->PBX, c->PBX * c->PBY, c->d_bricks);
         c->launches += 1;
     }
-    // offsets of the solid voxels only; the stale entries of empty voxels are cleared lazily (mat_normalize)
-    vt_fill_solid_kernel<<<grid_for((size_t)c->BX * c->BY * c->BZ, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_mat, X, Y, Z, c->BX, c->BY, c->BZ, c->PBX, c->PBX * c->PBY, fill);
-    c->launches += 1;
-    c->dist_valid = false;                             // acceleration structure of the renderer: rebuilt on its next use
-    c->mat_stale_empties = true;
-    c->n_emissive = 0;                                  // the volume was replaced: the old emissive list refers to nothing
     VT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    VT_CUDA(c, cudaMemsetAsync(c->d_ids, 0xff, n, c->stream));
+    vt_fill_solid_kernel<<<grid_for((size_t)c->BX * c->BY * c->BZ, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_ids, 1, X, Y, Z, c->BX, c->BY, c->BZ, c->PBX, c->PBX * c->PBY, 0);
+    c->launches += 1;
+    c->n_emissive = 0;                                  // the volume was replaced: the old emissive list refers to nothing
+    rc = rebuild_dist(c);
+    if (rc != VT_OK) return rc;
+    VT_CUDA(c, cudaEventRecord(c->ev2, c->stream));
     VT_CUDA(c, cudaGetLastError());
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
     VT_CUDA(c, cudaEventElapsedTime(&c->last_voxelize_ms, c->ev0, c->ev1));
-    cudaFree(d_xyz); cudaFree(d_idx); cudaFree(d_M);
+    VT_CUDA(c, cudaEventElapsedTime(&c->last_voxelize_full_ms, c->ev0, c->ev2));
     return VT_OK;
 }
 
 int vt_get_last_voxelize_ms(vt_ctx* c, float* ms) { if (!c || !ms) return VT_ERR_INVALID; *ms = c->last_voxelize_ms; return VT_OK; }
+int vt_get_last_voxelize_full_ms(vt_ctx* c, float* ms) { if (!c || !ms) return VT_ERR_INVALID; *ms = c->last_voxelize_full_ms; return VT_OK; }
 
 int vt_volume_assign_materials(vt_ctx* c, const int32_t* table, int n_table, int rule)
 {
     if (!c) return VT_ERR_INVALID;
     VT_REQ(c, table && n_table > 0 && rule == 1, "bad material rule");
+    VT_REQ(c, n_table <= 254, "rule-based assignment takes at most 254 material records");
+    VT_REQ(c, c->d_ids != nullptr, "no volume");
+    for (int i = 0; i < n_table; ++i) VT_REQ(c, table[i] >= 0, "material offsets must be >= 0");
     VT_BIND(c);
-    int* d_table = nullptr;
-    VT_CUDA(c, cudaMalloc(&d_table, n_table * sizeof(int)));
-    VT_CUDA(c, cudaMemcpyAsync(d_table, table, n_table * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    { const int rc = mat_normalize(c); if (rc != VT_OK) return rc; }
+    if (c->id_bytes != 1) {                               // a volume uploaded with > 255 records: narrow it first (every solid voxel gets a new id anyway)
+        std::vector<int32_t> grid((size_t)c->X * c->Y * c->Z);
+        int rc = vt_read_volume(c, grid.data());
+        if (rc != VT_OK) return rc;
+        for (auto& v : grid) if (v >= 0) v = table[0];
+        rc = vt_volume_upload(c, grid.data(), c->X, c->Y, c->Z);
+        if (rc != VT_OK) return rc;
+    }
+    // the ids become indices into the caller's table
+    int rc = set_id_table(c, std::vector<int32_t>(table, table + n_table));
+    if (rc != VT_OK) return rc;
     const size_t n = (size_t)c->X * c->Y * c->Z;
-    vt_assign_materials_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->d_mat, c->X, c->Y, c->Z, d_table, n_table, rule);
+    vt_assign_materials_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->d_ids, c->id_bytes, c->X, c->Y, c->Z, n_table, rule);
     c->launches += 1;
     VT_CUDA(c, cudaGetLastError());
     VT_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(d_table);
     return VT_OK;
 }
 
@@ -959,7 +1084,7 @@ int vt_add_voxel(vt_ctx* c, float mx, float my)
     if (!c) return VT_ERR_INVALID;
     int rc = need_frame(c); if (rc) return rc;
     VT_BIND(c);
-    vt_add_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), make_frame(c), mx, my, c->d_shared, c->d_mat, c->d_bricks, c->d_result);
+    vt_add_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), make_frame(c), mx, my, c->d_shared, c->d_ids, c->id_bytes, c->zero_id, c->d_bricks, c->d_result);
     c->launches += 1;
     VT_CUDA(c, cudaGetLastError());
     c->dist_valid = false;                                  // an empty cell may have become solid
@@ -969,7 +1094,7 @@ int vt_remove_voxel(vt_ctx* c)
 {
     if (!c) return VT_ERR_INVALID;
     VT_BIND(c);
-    vt_remove_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), c->d_shared, c->d_mat, c->d_bricks, c->d_result);
+    vt_remove_voxel_kernel<<<1, 32, 0, c->stream>>>(make_volume(c), c->d_shared, c->d_ids, c->id_bytes, c->d_bricks, c->d_result);
     c->launches += 1;
     VT_CUDA(c, cudaGetLastError());
     return VT_OK;

@@ -25,11 +25,12 @@ struct vt_ctx {
     // empty-space distance field over 8^3 cells (two buffers: the relaxation ping-pongs), see dda_skip
     unsigned char* d_dist[2] = {nullptr, nullptr}; int CX = 0, CY = 0, CZ = 0; int dist_cur = 0; bool dist_valid = false;   // dist_valid false: rebuilt before the next render that uses it
     int skip_mode = 1;                                     // 0 off, 1 auto (volumes with every side >= 64 voxels), 2 always
-    int32_t* d_mat = nullptr;
-    // vt_voxelize writes the offsets of the solid voxels only (as the reference's imageStore scatter does, voxelize.gs:111-116);
-    // the entries of empty voxels are then stale until mat_normalize() writes -1 into them -- done lazily, before the grid is
-    // exposed (vt_read_volume) or scanned (vt_volume_assign_materials). Rendering, picking and editing read solid voxels only.
-    bool mat_stale_empties = false;
+    // material ids: one byte per voxel (0xff = empty; two bytes, 0xffff = empty, when the volume has more than 255 distinct
+    // material records) + the table id -> offset; the reference's R32I offsets exist only at the boundary (vt_volume_upload /
+    // vt_read_volume). The record at offset 0 always has an id (`zero_id`): it is the material of the ground and of
+    // voxels added next to an empty selection (addVoxel.vs:37-40).
+    void* d_ids = nullptr; int id_bytes = 1; size_t ids_capacity = 0;
+    int32_t* d_id_offset = nullptr; std::vector<int32_t> h_id_offset; int zero_id = 0;
     unsigned long long* d_bricks_alloc = nullptr;         // padded array
     unsigned long long* d_bricks = nullptr;               // brick (0,0,0): d_bricks_alloc + 1 + PBX + PBX*PBY
     unsigned long long* d_bricks_empty = nullptr;         // template of the empty grid (sentinel shell only): clearing is one D2D copy
@@ -77,7 +78,8 @@ struct vt_ctx {
     Counters* d_counters = nullptr; bool count_enabled = false;
     uint64_t paths = 0, launches = 0;
     // voxelizer timing
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr; float last_voxelize_ms = 0.f, last_env_build_ms = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr; float last_voxelize_ms = 0.f, last_voxelize_full_ms = 0.f, last_env_build_ms = 0.f;
+    float* d_mesh_xyz = nullptr; unsigned int* d_mesh_idx = nullptr; float* d_mesh_M = nullptr; size_t mesh_verts_cap = 0, mesh_idx_cap = 0;
 };
 
 static inline int fail(vt_ctx* c, int code, const char* fmt, ...)

@@ -18,10 +18,14 @@ namespace vt {
 // shell in its next iteration: the stepping loop carries no bounds test, and the exit is told from a real hit after
 // the loop (dda_step). The DDA keeps a brick word in registers and touches memory only when the voxel moves to
 // another brick; the per-step arithmetic is identical to dda.h.
-// The int32 material-offset grid of the reference (R32I, x fastest, -1 empty) is kept as is
-// and read once per surface hit.
+// The reference's material-offset grid (R32I, x fastest, -1 empty: renderer.cpp:863-872) is stored as ONE BYTE per voxel: the
+// id of the voxel's material record (0xff = empty) + a table id -> offset (vt_volume_upload builds both; volumes with more
+// than 255 distinct records use 16-bit ids, 0xffff = empty). 128 MiB instead of 512 MiB at 512^3, 1 GiB instead of 4 GiB at
+// 1024^3; it is read once per surface hit (fetch_offset) and the table is a few cache lines.
 struct Volume {
-    const int32_t* __restrict__ mat;       // X*Y*Z material offsets
+    const uint8_t* __restrict__ ids8;      // X*Y*Z material ids, x fastest (nullptr when the volume uses 16-bit ids)
+    const uint16_t* __restrict__ ids16;
+    const int32_t* __restrict__ id_offset; // id -> offset into the material array
     const unsigned long long* __restrict__ bricks;   // brick (0,0,0) of the padded array
     int X, Y, Z;
     int BX, BXY;                           // strides of the padded brick array
@@ -146,10 +150,26 @@ VT_DEV bool out_of_grid(f3 p, f3 resf)
 {
     return (p.x < 0.0f) || (p.y < 0.0f) || (p.z < 0.0f) || (p.x >= resf.x) || (p.y >= resf.y) || (p.z >= resf.z);
 }
+VT_DEV int fetch_id(const Volume& V, size_t i)                    // material id of voxel i, -1 = empty
+{
+    if (V.ids8 != nullptr) { const int v = (int)__ldg(V.ids8 + i); return v == 0xff ? -1 : v; }
+    const int v = (int)__ldg(V.ids16 + i);
+    return v == 0xffff ? -1 : v;
+}
 VT_DEV int fetch_offset(const Volume& V, int x, int y, int z)     // texelFetch(materialOffsetTexture); out of range -> 0
 {
     if ((unsigned)x >= (unsigned)V.X || (unsigned)y >= (unsigned)V.Y || (unsigned)z >= (unsigned)V.Z) return 0;
-    return __ldg(V.mat + ((size_t)x + (size_t)y * (size_t)V.X + (size_t)z * (size_t)V.X * (size_t)V.Y));
+    const int id = fetch_id(V, (size_t)x + (size_t)y * (size_t)V.X + (size_t)z * (size_t)V.X * (size_t)V.Y);
+    return id < 0 ? -1 : __ldg(V.id_offset + id);
+}
+VT_DEV void prefetch_id(const Volume& V, size_t i)
+{
+    prefetch_l1(V.ids8 != nullptr ? (const void*)(V.ids8 + i) : (const void*)(V.ids16 + i));
+}
+VT_DEV void store_id(void* ids, int id_bytes, size_t i, int id)   // id < 0: empty
+{
+    if (id_bytes == 1) reinterpret_cast<uint8_t*>(ids)[i] = (uint8_t)(id < 0 ? 0xff : id);
+    else reinterpret_cast<uint16_t*>(ids)[i] = (uint16_t)(id < 0 ? 0xffff : id);
 }
 
 // Literal float-state restatement of dda.h:38-57, used only when the start voxel is NaN

@@ -126,7 +126,7 @@ VT_DEV void set_voxel_bits(unsigned long long* bricks, const Volume& V, int x, i
 
 // addVoxel.vs:16-41. result[0] = 1 if a voxel was written, result[1..3] = its coordinate.
 VT_GLOBAL void vt_add_voxel_kernel(const Volume V, const Frame F, float mx, float my, const Shared* sh,
-                                    int* mat, unsigned long long* bricks, int* result)
+                                    void* ids, int id_bytes, int zero_id, unsigned long long* bricks, int* result)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const f3 right = xyz(mul44(F.inv_mv, 1.0f, 0.0f, 0.0f, 0.0f));     // :18
@@ -147,51 +147,49 @@ VT_GLOBAL void vt_add_voxel_kernel(const Volume V, const Frame F, float mx, floa
     const int cz = sh->sel_index[2] + f2i(normal.z);
     result[0] = 0; result[1] = cx; result[2] = cy; result[3] = cz;
     if ((unsigned)cx >= (unsigned)V.X || (unsigned)cy >= (unsigned)V.Y || (unsigned)cz >= (unsigned)V.Z) return;
-    // :37-40 material of the selected voxel, the ground's (offset 0) when that voxel is empty. Emptiness is read from the
-    // occupancy bits: the offset entries of empty voxels may be stale (vt_voxelize)
+    // :37-40 material of the selected voxel, the ground's (the record at offset 0: its id is `zero_id`) when that voxel is empty
     const int sx = sh->sel_index[0], sy = sh->sel_index[1], sz = sh->sel_index[2];
-    int off = 0;
-    if ((unsigned)sx < (unsigned)V.X && (unsigned)sy < (unsigned)V.Y && (unsigned)sz < (unsigned)V.Z) {
-        const unsigned long long w = bricks[(sx >> 2) + (sy >> 2) * V.BX + (sz >> 2) * V.BXY];
-        if ((w >> ((sx & 3) | ((sy & 3) << 2) | ((sz & 3) << 4))) & 1ull) off = fetch_offset(V, sx, sy, sz);
-    }
-    if (off < 0) off = 0;
-    mat[(size_t)cx + (size_t)cy * V.X + (size_t)cz * V.X * V.Y] = off;
+    int id = -1;
+    if ((unsigned)sx < (unsigned)V.X && (unsigned)sy < (unsigned)V.Y && (unsigned)sz < (unsigned)V.Z)
+        id = fetch_id(V, (size_t)sx + (size_t)sy * V.X + (size_t)sz * V.X * V.Y);
+    if (id < 0) id = zero_id;
+    store_id(ids, id_bytes, (size_t)cx + (size_t)cy * V.X + (size_t)cz * V.X * V.Y, id);
     set_voxel_bits(bricks, V, cx, cy, cz, true);
     result[0] = 1;
 }
 
 // removeVoxel.vs:8-11 (contract N2: the voxel becomes empty)
 VT_GLOBAL void vt_remove_voxel_kernel(const Volume V, const Shared* sh,
-                                       int* mat, unsigned long long* bricks, int* result)
+                                       void* ids, int id_bytes, unsigned long long* bricks, int* result)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int x = sh->sel_index[0], y = sh->sel_index[1], z = sh->sel_index[2];
     result[0] = 0; result[1] = x; result[2] = y; result[3] = z;
     if ((unsigned)x >= (unsigned)V.X || (unsigned)y >= (unsigned)V.Y || (unsigned)z >= (unsigned)V.Z) return;
-    mat[(size_t)x + (size_t)y * V.X + (size_t)z * V.X * V.Y] = -1;
+    store_id(ids, id_bytes, (size_t)x + (size_t)y * V.X + (size_t)z * V.X * V.Y, -1);
     set_voxel_bits(bricks, V, x, y, z, false);
     result[0] = 1;
 }
 
 // ---- occupancy layout ------------------------------------------------------------------------
-// one thread per (brick, z-slice-of-4): builds 16 bits; a 4-thread group ORs them with shuffles.
-// Simpler and fast enough (upload-time only): one thread per brick row (4 voxels in x) -> atomicOr.
-VT_GLOBAL void vt_build_bricks_kernel(const int* __restrict__ mat, unsigned long long* __restrict__ bricks,
+// bit-packed occupancy from the material ids: one thread per brick row (4 voxels in x) -> atomicOr.
+VT_GLOBAL void vt_build_bricks_kernel(const void* __restrict__ ids, int id_bytes, unsigned long long* __restrict__ bricks,
                                        int X, int Y, int Z, int BX, int PBX, int BXY)
 {
-    // thread -> (bx, y, z): reads up to 4 consecutive ints
     const size_t n = (size_t)BX * (size_t)Y * (size_t)Z;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int bx = (int)(i % BX);
         const size_t r = i / BX;
         const int y = (int)(r % Y), z = (int)(r / Y);
         const int x0 = bx << 2;
-        const int* row = mat + ((size_t)x0 + (size_t)y * X + (size_t)z * X * Y);
+        const size_t at = (size_t)x0 + (size_t)y * X + (size_t)z * X * Y;
         unsigned int m = 0;
         #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (x0 + k < X && __ldg(row + k) >= 0) m |= 1u << k;
+        for (int k = 0; k < 4; ++k) {
+            if (x0 + k >= X) continue;
+            const bool solid = (id_bytes == 1) ? (reinterpret_cast<const uint8_t*>(ids)[at + k] != 0xff) : (reinterpret_cast<const uint16_t*>(ids)[at + k] != 0xffff);
+            if (solid) m |= 1u << k;
+        }
         if (m) {
             const int sh = ((y & 3) << 2) | ((z & 3) << 4);
             atomicOr(bricks + ((long long)bx + (long long)(y >> 2) * PBX + (long long)(z >> 2) * BXY), (unsigned long long)m << sh);
@@ -260,49 +258,10 @@ VT_GLOBAL void vt_dist_pass_kernel(const unsigned char* __restrict__ in, unsigne
     }
 }
 
-// material-offset grid from occupancy: voxel = bit ? fill : -1. One thread per x-run of 4 voxels.
-VT_GLOBAL void vt_fill_offsets_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
-                                       int X, int Y, int Z, int BX, int PBX, int BXY, int fill)
-{
-    const size_t n = (size_t)BX * (size_t)Y * (size_t)Z;
-    const bool vec = (X & 3) == 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int bx = (int)(i % BX);
-        const size_t r = i / BX;
-        const int y = (int)(r % Y), z = (int)(r / Y);
-        const unsigned long long b = __ldg(bricks + ((long long)bx + (long long)(y >> 2) * PBX + (long long)(z >> 2) * BXY));
-        const unsigned int m = (unsigned int)(b >> (((y & 3) << 2) | ((z & 3) << 4))) & 0xfu;
-        int* row = mat + ((size_t)(bx << 2) + (size_t)y * X + (size_t)z * X * Y);
-        if (vec) {
-            int4 v;
-            v.x = (m & 1u) ? fill : -1; v.y = (m & 2u) ? fill : -1; v.z = (m & 4u) ? fill : -1; v.w = (m & 8u) ? fill : -1;
-            *reinterpret_cast<int4*>(row) = v;
-        } else {
-            for (int k = 0; k < 4; ++k) if ((bx << 2) + k < X) row[k] = ((m >> k) & 1u) ? fill : -1;
-        }
-    }
-}
-
-// lazy counterpart of vt_fill_solid_kernel: writes -1 into every voxel whose occupancy bit is clear (one thread per x-run of 4)
-VT_GLOBAL void vt_clear_empty_offsets_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
-                                              int X, int Y, int Z, int BX, int PBX, int BXY)
-{
-    const size_t n = (size_t)BX * (size_t)Y * (size_t)Z;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int bx = (int)(i % BX);
-        const size_t r = i / BX;
-        const int y = (int)(r % Y), z = (int)(r / Y);
-        const unsigned long long b = __ldg(bricks + ((long long)bx + (long long)(y >> 2) * PBX + (long long)(z >> 2) * BXY));
-        const unsigned int m = (unsigned int)(b >> (((y & 3) << 2) | ((z & 3) << 4))) & 0xfu;
-        int* row = mat + ((size_t)(bx << 2) + (size_t)y * X + (size_t)z * X * Y);
-        for (int k = 0; k < 4; ++k) if ((bx << 2) + k < X && !((m >> k) & 1u)) row[k] = -1;
-    }
-}
-
-// sparse variant used by vt_voxelize: the grid was cleared to -1 by a memset; one thread per brick patches `fill` into the
-// voxels whose bit is set (in-volume bits only: boundary bricks also carry sentinel bits)
-VT_GLOBAL void vt_fill_solid_kernel(const unsigned long long* __restrict__ bricks, int* __restrict__ mat,
-                                     int X, int Y, int Z, int BX, int BY, int BZ, int PBX, int BXY, int fill)
+// used by vt_voxelize: the id grid was cleared to "empty" by a memset; one thread per brick writes `id` into the voxels whose
+// bit is set (in-volume bits only: boundary bricks also carry sentinel bits)
+VT_GLOBAL void vt_fill_solid_kernel(const unsigned long long* __restrict__ bricks, void* __restrict__ ids, int id_bytes,
+                                     int X, int Y, int Z, int BX, int BY, int BZ, int PBX, int BXY, int id)
 {
     const size_t n = (size_t)BX * BY * BZ;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -313,7 +272,7 @@ VT_GLOBAL void vt_fill_solid_kernel(const unsigned long long* __restrict__ brick
             const int k = __ffsll((long long)w) - 1;
             w &= w - 1ull;
             const int x = bx * 4 + (k & 3), y = by * 4 + ((k >> 2) & 3), z = bz * 4 + (k >> 4);
-            if (x < X && y < Y && z < Z) mat[(size_t)x + (size_t)y * X + (size_t)z * X * Y] = fill;
+            if (x < X && y < Y && z < Z) store_id(ids, id_bytes, (size_t)x + (size_t)y * X + (size_t)z * X * Y, id);
         }
     }
 }
@@ -412,16 +371,16 @@ vt_voxelize_kernel(const float* __restrict__ xyz_in, const unsigned int* __restr
 
 // rule-based material assignment for solid voxels (BASELINE config 3):
 // rule 1: id = ((x>>5) ^ (y>>5) ^ (z>>5)) % n_table
-VT_GLOBAL void vt_assign_materials_kernel(int* __restrict__ mat, int X, int Y, int Z,
-                                           const int* __restrict__ table, int n_table, int rule)
+VT_GLOBAL void vt_assign_materials_kernel(void* __restrict__ ids, int id_bytes, int X, int Y, int Z, int n_table, int rule)
 {
     const size_t n = (size_t)X * Y * Z;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (mat[i] < 0) continue;
+        const bool solid = (id_bytes == 1) ? (reinterpret_cast<const uint8_t*>(ids)[i] != 0xff) : (reinterpret_cast<const uint16_t*>(ids)[i] != 0xffff);
+        if (!solid) continue;
         const int x = (int)(i % X); const size_t r = i / X; const int y = (int)(r % Y), z = (int)(r / Y);
         int id = 0;
         if (rule == 1) id = ((x >> 5) ^ (y >> 5) ^ (z >> 5)) % n_table;
-        mat[i] = __ldg(table + id);
+        store_id(ids, id_bytes, i, id);                     // the id IS the index into the caller's offset table
     }
 }
 

@@ -583,7 +583,7 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const int gen, W
             {   // gathers whose addresses are known now but whose values are needed hundreds of instructions later
                 if ((unsigned)rng.x < (unsigned)F.noise_w && (unsigned)rng.y < (unsigned)F.noise_h) prefetch_keep(F.noise + ((size_t)rng.x + (size_t)rng.y * (size_t)F.noise_w));
                 if ((unsigned)hx < (unsigned)V.X && (unsigned)hy < (unsigned)V.Y && (unsigned)hz < (unsigned)V.Z)
-                    prefetch_l1(V.mat + ((size_t)hx + (size_t)hy * (size_t)V.X + (size_t)hz * (size_t)V.X * (size_t)V.Y));
+                    prefetch_id(V, (size_t)hx + (size_t)hy * (size_t)V.X + (size_t)hz * (size_t)V.X * (size_t)V.Y);
             }
             const f3 ro = mk3(r01.lo.x, r01.lo.y, r01.lo.z), rd = mk3(r01.lo.w, r01.hi.x, r01.hi.y);
             const float bsdf_pdf = r01.hi.z;
