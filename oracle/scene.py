@@ -92,9 +92,12 @@ def parse_vox(data):
     return size, voxels, palette
 
 
-def load_vox(path_or_bytes):
+def load_vox(path_or_bytes, palette_rules=None):
     """MagicaVoxelLoader::load (declared 5-arg contract, SURVEY N1).
-    Returns dict(res=(X,Y,Z), grid int32[X*Y*Z] x-fastest, materials float32[], emissive int32[])."""
+    Returns dict(res=(X,Y,Z), grid int32[X*Y*Z] x-fastest, materials float32[], emissive int32[]).
+    palette_rules (new-build extension, not in the reference): [(colour index, type 0/1/2, (er, eg, eb), roughness)] turns a
+    palette entry into a Lambert / Metal / Plastic record with emission; records are [type][emission][colour]([roughness])."""
+    rules = {int(r[0]): r for r in (palette_rules or [])}
     data = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray)) else read_bytes(path_or_bytes)
     (sx, sy, sz), voxels, palette = parse_vox(data)
     X, Y, Z = sx, sz, sy                                   # magicaVoxel.cpp:276-278 (y<->z)
@@ -109,7 +112,11 @@ def load_vox(path_or_bytes):
         if mat_off[ci] < 0:                                # :300-318
             mat_off[ci] = len(materials)
             albedo = [f32(pal[ci, k]) / f32(255) for k in range(3)]
-            materials.extend([f32(0), f32(0), f32(0), f32(0)] + albedo)   # [type=0][emission][albedo]
+            if ci in rules:
+                _, mt, em, rough = rules[ci]
+                materials.extend([f32(mt)] + [f32(v) for v in em] + albedo + ([f32(rough)] if int(mt) in (1, 2) else []))
+            else:
+                materials.extend([f32(0), f32(0), f32(0), f32(0)] + albedo)   # [type=0][emission][albedo]
         grid[off] = mat_off[ci]
     materials = np.array(materials, np.float32)
     emissive = emissive_voxels(grid, materials)

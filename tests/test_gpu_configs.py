@@ -151,8 +151,8 @@ def test_empty_space_skip_is_bit_identical(vt_ctx):
     vt_ctx.set_empty_skip(1)
 
 
-def test_advance_until_closed_form_equals_literal_loop(vt_ctx):
-    """advance_until (the O(binades) form of `while (d <= tau && k < nmax) d += e`) against the literal loop on the device,
+def test_advance_until_equals_literal_loop(vt_ctx):
+    """advance_until (`while (d <= tau && k < nmax) d += e`, four additions per trip) against the literal loop on the device,
     on realistic DDA operands and on adversarial ones (exact ties, power-of-two increments, tiny/huge ratios, zero start)."""
     rng = np.random.RandomState(5)
     n = 400000

@@ -153,3 +153,57 @@ def test_png_writer_round_trip(host, tmp_path):
         p = str(tmp_path / ("t%dx%d.png" % (w, h)))
         host.write_png(p, img)
         assert np.array_equal(_decode_png(p), img)
+
+
+def test_magicavoxel_corrupt_chunk_sizes_are_rejected(host, tmp_path):
+    """chunk sizes come from the file. Negative sizes (the cursor would stand still or move backwards: an endless
+    loop), and chunks that end beyond MAIN or beyond the file, must fail with 'corrupt chunk' instead of hanging."""
+    import signal
+
+    def vox(chunks, main_children=None):
+        return b"VOX " + struct.pack("<i", 150) + b"MAIN" + struct.pack("<ii", 0, len(chunks) if main_children is None else main_children) + chunks
+
+    size = b"SIZE" + struct.pack("<ii", 12, 0) + struct.pack("<iii", 2, 2, 2)
+    cases = {
+        "negative content size": vox(size + b"PACK" + struct.pack("<ii", -12, 0) + b"\0" * 8),
+        "negative children size": vox(size + b"PACK" + struct.pack("<ii", 0, -24)),
+        "chunk beyond MAIN": vox(size + b"XYZI" + struct.pack("<ii", 4000, 0) + struct.pack("<i", 0)),
+        "MAIN with negative size": b"VOX " + struct.pack("<i", 150) + b"MAIN" + struct.pack("<ii", -4, 100) + size,
+    }
+    old = signal.signal(signal.SIGALRM, lambda *_: (_ for _ in ()).throw(TimeoutError("load_vox hung")))
+    try:
+        for name, data in cases.items():
+            p = str(tmp_path / "bad.vox")
+            with open(p, "wb") as f:
+                f.write(data)
+            signal.alarm(10)
+            with pytest.raises(IOError):
+                host.load_vox(p)
+            signal.alarm(0)
+    finally:
+        signal.alarm(0); signal.signal(signal.SIGALRM, old)
+    # MAIN may announce more children bytes than the file holds (truncated download): what is there is still read
+    p = str(tmp_path / "short.vox")
+    with open(p, "wb") as f:
+        f.write(vox(size + b"XYZI" + struct.pack("<ii", 8, 0) + struct.pack("<i", 1) + struct.pack("<4B", 1, 1, 1, 7), main_children=4096))
+    got = host.load_vox(p)
+    assert tuple(got["res"]) == (2, 2, 2) and (got["grid"] >= 0).sum() == 1
+
+
+def test_magicavoxel_palette_rules_match_oracle(host, tmp_path):
+    """New-build extension: palette index -> Lambert / Metal / Plastic record with emission and roughness; the
+    record layouts are the reference's (material/material.h:15-33), the emissive list follows voxLoader.h:23-24."""
+    rng = np.random.RandomState(4)
+    vox = [(int(x), int(y), int(z), int(c)) for x, y, z, c in zip(rng.randint(0, 6, 80), rng.randint(0, 6, 80),
+                                                                     rng.randint(0, 6, 80), rng.choice([3, 9, 17, 40, 200], 80))]
+    p = str(tmp_path / "rules.vox")
+    _write_vox(p, (6, 6, 6), vox)
+    rules = [(9, host.MT_METAL, (0.0, 0.0, 0.0), 120.0), (17, host.MT_LAMBERT, (4.0, 3.0, 2.0), 0.0),
+             (40, host.MT_PLASTIC, (0.5, 0.0, 0.0), 35.0), (99, host.MT_METAL, (1.0, 1.0, 1.0), 5.0)]      # 99: unused colour
+    got, ref = host.load_vox(p, palette_rules=rules), oscene.load_vox(p, palette_rules=rules)
+    assert np.array_equal(got["grid"], ref["grid"]) and np.array_equal(got["materials"], ref["materials"])
+    assert np.array_equal(got["emissive"], ref["emissive"]) and got["emissive"].size > 0
+    types = sorted(set(int(got["materials"][o]) for o in np.unique(got["grid"][got["grid"] >= 0])))
+    assert types == [0, 1, 2]
+    plain = host.load_vox(p)
+    assert np.array_equal(plain["materials"], oscene.load_vox(p)["materials"]) and plain["emissive"].size == 0

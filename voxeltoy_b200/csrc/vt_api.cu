@@ -103,7 +103,8 @@ void vt_destroy(vt_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_ids); cudaFree(c->d_id_offset); cudaFree(c->d_bricks_alloc); cudaFree(c->d_bricks_empty); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]); cudaFree(c->d_materials); cudaFree(c->d_emissive);
+    cudaFree(c->d_ids); cudaFree(c->d_id_offset); cudaFree(c->d_bricks_alloc); cudaFree(c->d_bricks_empty); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]); cudaFree(c->d_dist4[0]); cudaFree(c->d_dist4[1]); cudaFree(c->d_skip);
+    cudaFree(c->d_materials); cudaFree(c->d_emissive);
     cudaFree(c->d_noise); cudaFree(c->d_env); cudaFree(c->d_cdf_u); cudaFree(c->d_cdf_v); cudaFree(c->d_accum); cudaFree(c->d_display);
     cudaFree(c->d_guide_v); cudaFree(c->d_guide_u);
     for (int k = 0; k < vt_ctx::kWfLanes; ++k) {
@@ -180,19 +181,25 @@ static int alloc_volume(vt_ctx* c, int X, int Y, int Z)
         const int BX = (X + 3) / 4, BY = (Y + 3) / 4, BZ = (Z + 3) / 4, PBX = BX + 2, PBY = BY + 2, PBZ = BZ + 2;
         const int CX = (X + 7) / 8, CY = (Y + 7) / 8, CZ = (Z + 7) / 8;
         const size_t npb = (size_t)PBX * PBY * PBZ, nc = (size_t)CX * CY * CZ;
-        unsigned long long *bricks = nullptr, *empty = nullptr; unsigned char *d0 = nullptr, *d1 = nullptr;
+        unsigned long long *bricks = nullptr, *empty = nullptr; unsigned char *d0 = nullptr, *d1 = nullptr, *f0 = nullptr, *f1 = nullptr, *sk = nullptr;
+        const size_t nb = (size_t)BX * BY * BZ;
         cudaError_t e = cudaMalloc(&bricks, npb * 8);
         if (e == cudaSuccess) e = cudaMalloc(&empty, npb * 8);
         if (e == cudaSuccess) e = cudaMalloc(&d0, nc);
         if (e == cudaSuccess) e = cudaMalloc(&d1, nc);
+        if (e == cudaSuccess) e = cudaMalloc(&f0, nb);
+        if (e == cudaSuccess) e = cudaMalloc(&f1, nb);
+        if (e == cudaSuccess) e = cudaMalloc(&sk, nb);
         if (e != cudaSuccess) {
-            cudaFree(bricks); cudaFree(empty); cudaFree(d0); cudaFree(d1); cudaGetLastError();
+            cudaFree(bricks); cudaFree(empty); cudaFree(d0); cudaFree(d1); cudaFree(f0); cudaFree(f1); cudaFree(sk); cudaGetLastError();
             return fail(c, VT_ERR_CUDA, "volume %dx%dx%d: %s", X, Y, Z, cudaGetErrorString(e));
         }
         VT_CUDA(c, cudaStreamSynchronize(c->stream));
         cudaFree(c->d_ids); cudaFree(c->d_bricks_alloc); cudaFree(c->d_bricks_empty); cudaFree(c->d_dist[0]); cudaFree(c->d_dist[1]);
+        cudaFree(c->d_dist4[0]); cudaFree(c->d_dist4[1]); cudaFree(c->d_skip);
         c->d_ids = nullptr; c->ids_capacity = 0;
         c->d_bricks_alloc = bricks; c->d_bricks_empty = empty; c->d_dist[0] = d0; c->d_dist[1] = d1; c->dist_valid = false;
+        c->d_dist4[0] = f0; c->d_dist4[1] = f1; c->d_skip = sk;
         c->X = X; c->Y = Y; c->Z = Z;
         c->BX = BX; c->BY = BY; c->BZ = BZ; c->PBX = PBX; c->PBY = PBY; c->PBZ = PBZ; c->CX = CX; c->CY = CY; c->CZ = CZ;
         c->d_bricks = c->d_bricks_alloc + (1 + (size_t)PBX + (size_t)PBX * PBY);
@@ -215,19 +222,29 @@ static int clear_occupancy(vt_ctx* c)
     return VT_OK;
 }
 
-// (re)builds the empty-space distance field from the bricks. Cheap (the cell grid is 1/512 of the voxels): run after every
-// change that can make an empty cell solid (upload, voxelize, add voxel). Removing voxels leaves it valid (lower bounds).
-static constexpr int kDistCap = 16;
+// (re)builds the empty-space skip field from the bricks: the far field over 8^3 cells (cap 16), the near field over 4^3 bricks
+// (cap 3) and the byte per brick the DDA reads. Cheap (one byte per 64 voxels): run after every change that can make an empty
+// cell solid (upload, voxelize, add voxel). Removing voxels leaves it valid (lower bounds).
+#ifndef VT_DIST_CAP
+#define VT_DIST_CAP 16
+#endif
+static constexpr int kDistCap = VT_DIST_CAP, kDist4Cap = 3;      // kDistCap <= 63 (6 bits of the skip byte)
 static int rebuild_dist(vt_ctx* c)
 {
-    const size_t nc = (size_t)c->CX * c->CY * c->CZ;
+    const size_t nc = (size_t)c->CX * c->CY * c->CZ, nb = (size_t)c->BX * c->BY * c->BZ;
     vt_dist_init_kernel<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_dist[0], c->X, c->Y, c->Z, c->PBX, c->PBX * c->PBY,
                                                                  c->CX, c->CY, c->CZ, kDistCap);
     int cur = 0;
     for (int axis = 0; axis < 3; ++axis, cur ^= 1)
         vt_dist_pass_kernel<<<grid_for(nc, 256), 256, 0, c->stream>>>(c->d_dist[cur], c->d_dist[cur ^ 1], c->CX, c->CY, c->CZ, axis, kDistCap);
+    vt_dist4_init_kernel<<<grid_for(nb, 256), 256, 0, c->stream>>>(c->d_bricks, c->d_dist4[0], c->X, c->Y, c->Z, c->PBX, c->PBX * c->PBY,
+                                                                  c->BX, c->BY, c->BZ, kDist4Cap);
+    int cur4 = 0;
+    for (int axis = 0; axis < 3; ++axis, cur4 ^= 1)
+        vt_dist_pass_kernel<<<grid_for(nb, 256), 256, 0, c->stream>>>(c->d_dist4[cur4], c->d_dist4[cur4 ^ 1], c->BX, c->BY, c->BZ, axis, kDist4Cap);
+    vt_skip_combine_kernel<<<grid_for(nb, 256), 256, 0, c->stream>>>(c->d_dist[cur], c->d_dist4[cur4], c->d_skip, c->BX, c->BY, c->BZ, c->CX, c->CY);
     c->dist_cur = cur; c->dist_valid = true;
-    c->launches += 4;
+    c->launches += 9;
     VT_CUDA(c, cudaGetLastError());
     return VT_OK;
 }
@@ -616,7 +633,7 @@ static Volume make_volume(const vt_ctx* c)
     V.X = c->X; V.Y = c->Y; V.Z = c->Z;
     V.BX = c->PBX; V.BXY = c->PBX * c->PBY;               // strides of the padded brick array
     const bool skip = c->dist_valid && skip_wanted(c);
-    V.dist = skip ? c->d_dist[c->dist_cur] : nullptr; V.CX = c->CX; V.CXY = c->CX * c->CY;
+    V.skip = skip ? c->d_skip : nullptr; V.SX = c->BX; V.SXY = c->BX * c->BY;
     V.bmin.x = c->bmin[0]; V.bmin.y = c->bmin[1]; V.bmin.z = c->bmin[2];
     V.bmax.x = c->bmax[0]; V.bmax.y = c->bmax[1]; V.bmax.z = c->bmax[2];
     V.vsize.x = c->vsize[0]; V.vsize.y = c->vsize[1]; V.vsize.z = c->vsize[2];
@@ -837,7 +854,7 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
             // of generation `it`, block it + 1 the shade queues wf_trace fills.
             if (it > 0) { WfTimer t(c, VT_K_OTHER, st); VT_CUDA(c, cudaMemsetAsync(S.vis, 0, vis_bytes, st)); }
             { WfTimer t(c, VT_K_TRACE, st);
-              if (V.dist != nullptr && !COUNT) wf_trace_kernel<COUNT, true><<<c->wf_trace_blocks[ci], kWfTraceThreads, 0, st>>>(V, F, S, it == 0 ? 1 : 0, cn + it, cn + it + 1, c->d_counters);
+              if (V.skip != nullptr && !COUNT) wf_trace_kernel<COUNT, true><<<c->wf_trace_blocks[ci], kWfTraceThreads, 0, st>>>(V, F, S, it == 0 ? 1 : 0, cn + it, cn + it + 1, c->d_counters);
               else wf_trace_kernel<COUNT, false><<<c->wf_trace_blocks[ci], kWfTraceThreads, 0, st>>>(V, F, S, it == 0 ? 1 : 0, cn + it, cn + it + 1, c->d_counters); }
             c->launches += 1;
             if (it == 0 && prim != nullptr && pass0 + nb == L.n_passes) {

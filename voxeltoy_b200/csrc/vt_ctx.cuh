@@ -24,6 +24,8 @@ struct vt_ctx {
     int PBX = 0, PBY = 0, PBZ = 0;                         // padded brick counts (strides)
     // empty-space distance field over 8^3 cells (two buffers: the relaxation ping-pongs), see dda_skip
     unsigned char* d_dist[2] = {nullptr, nullptr}; int CX = 0, CY = 0, CZ = 0; int dist_cur = 0; bool dist_valid = false;   // dist_valid false: rebuilt before the next render that uses it
+    unsigned char* d_dist4[2] = {nullptr, nullptr};        // near field over 4^3 bricks (ping-pong), capped at 3
+    unsigned char* d_skip = nullptr;                       // what the DDA reads: one byte per brick, both levels (Volume::skip)
     int skip_mode = 1;                                     // 0 off, 1 auto (volumes with every side >= 64 voxels), 2 always
     // material ids: one byte per voxel (0xff = empty; two bytes, 0xffff = empty, when the volume has more than 255 distinct
     // material records) + the table id -> offset; the reference's R32I offsets exist only at the boundary (vt_volume_upload /

@@ -29,9 +29,11 @@ struct Volume {
     const unsigned long long* __restrict__ bricks;   // brick (0,0,0) of the padded array
     int X, Y, Z;
     int BX, BXY;                           // strides of the padded brick array
-    // empty-space distance field over 8^3-voxel cells (dda_skip): 0 = cell holds a solid voxel, k >= 1 = every cell within
-    // Chebyshev distance k-1 is empty (capped). nullptr = skipping disabled for this volume.
-    const unsigned char* __restrict__ dist; int CX, CXY;
+    // empty-space skip field (dda_skip), one byte per 4^3 brick (unpadded, x fastest): bits 2..7 = k8, the Chebyshev distance
+    // field over 8^3-voxel cells (0 = the cell holds a solid voxel, k >= 1 = every cell within distance k-1 is empty, capped);
+    // bits 0..1 = k4, the same over 4^3 bricks capped at 3 (the near field: thin shells leave rays within two 8^3 cells of a
+    // surface for long stretches). nullptr = skipping disabled for this volume.
+    const unsigned char* __restrict__ skip; int SX, SXY;
     f3 bmin, bmax, vsize, resf;            // world bounds, wsVoxelSize, vec3(voxelResolution)
     f3 inv_extent;                         // 1.0 / (bmax - bmin)  (dda.h:16, hoisted: same IEEE divisions on the host)
     int max_steps;                         // dda.h:98
@@ -310,74 +312,53 @@ VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
 // be empty, the iteration order of dda.h:51 is a merge of three increasing sequences D_a(j+1) = fl(D_a(j) + e_a): each
 // iteration advances every axis whose D equals the current minimum. The state reached after all values <= tau have been
 // processed is therefore, for ANY threshold tau, (i_a + s_a k_a, D_a(k_a)) with k_a = #{j : D_a(j) <= tau} -- computable
-// per axis with the same float additions and nothing else (2 instructions per skipped step instead of ~40). tau is placed
-// just below the first value at which some axis would leave the box; the per-axis step limits verify that no axis left
-// (otherwise the skip is abandoned with the state untouched), and the ordinary loop takes over for the last few steps.
-// The box comes from the distance field of Volume: cube of (2k-1) cells around the ray's cell, clipped to the volume.
+// per axis with the same float additions and nothing else. tau is placed just below the first value at which some axis would
+// leave the box; the per-axis step limits verify that no axis left (otherwise the skip is abandoned with the state
+// untouched), and the ordinary loop takes over for the last few steps.
+// The box comes from the distance fields of Volume: a cube of (2k-1) cells around the ray's cell, clipped to the volume.
 //
-// advance_until: d <- fl(d + e) while d <= tau, at most nmax times; returns the number of additions. Exact, in O(binades
-// crossed) instead of O(additions): inside one binade (ulp u) a rounded addition of the constant e moves the 24-bit
-// significand by a constant integer c -- e = (q + rem / 2^sh) u with sh = exponent(d) - exponent(e); c = q when rem is below
-// half an ulp, q + 1 above, and on an exact tie round-half-even settles (once the significand is even) on q + (q & 1). So
-// t additions are M += t c as long as the significand stays below 2^24; the addition that crosses into the next binade is
-// done with the real instruction. Anything unusual (zero, denormals, e >= d) takes single real additions.
+// advance_until: d <- fl(d + e) while d <= tau, at most nmax times; returns the number of additions. The additions are simply
+// performed, four per trip: 2 instructions per skipped addition against 27 for a full DDA step. The values increase
+// monotonically (e > 0), so four additions may be taken at once iff the third result is still <= tau.
+// (Round 1 replaced long runs by a closed form -- inside one binade a rounded addition of a constant moves the significand by
+// a constant integer -- but its set-up ran on ~8 lanes per instruction and was 54 % of wf_trace's instructions on the 512^3
+// bunny, profiles/r02_c3_v17_*; with the distance field capped at 16 cells a run is at most 127 additions = 32 trips.)
 VT_DEV int advance_until(float& d, float e, float tau, int nmax)
 {
     int k = 0;
-    // a handful of additions: the plain loop (3 instructions per addition) beats the set-up below. The estimate is only a hint.
-    if (!(__fdividef(tau - d, e) > 6.0f)) {
-        while (d <= tau && k < nmax) { d = d + e; ++k; }
-        return k;
+    while (k + 4 <= nmax) {
+        const float a1 = d + e, a2 = a1 + e, a3 = a2 + e;
+        if (!(a3 <= tau)) break;
+        d = a3 + e; k += 4;
     }
-    #pragma unroll 1
-    for (int guard = 0; guard < 48; ++guard) {
-        if (!(d <= tau) || k >= nmax) return k;
-        const unsigned int xb = (unsigned int)__float_as_int(d), eb = (unsigned int)__float_as_int(e), tb = (unsigned int)__float_as_int(tau);
-        const int E = (int)(xb >> 23), Ee = (int)(eb >> 23), Et = (int)(tb >> 23);      // d, e, tau > 0: no sign bits
-        const int sh = E - Ee;
-        unsigned int t = 0u;                                      // additions done by moving the significand
-        if (sh >= 25 && E < 255) return nmax;                     // e < u/2: d + e == d for ever
-        if (E != 0 && Ee != 0 && E < 255 && sh > 0) {
-            const unsigned int M = (xb & 0x7fffffu) | 0x800000u, Me = (eb & 0x7fffffu) | 0x800000u;
-            const unsigned int q = Me >> sh, rem = Me & ((1u << sh) - 1u), half = 1u << (sh - 1);
-            const bool tie = (rem == half);
-            const unsigned int c = tie ? q + (q & 1u) : q + (rem > half ? 1u : 0u);
-            if (c == 0u) return nmax;                             // sh == 24 and e == u/2 exactly: stuck (round half to even)
-            if (!(tie && (M & 1u))) {                             // on a tie the parity settles after one real addition
-                // additions whose result stays <= tau and inside this binade
-                const unsigned int lim = (Et == E) ? ((tb & 0x7fffffu) | 0x800000u) : 0xFFFFFFu;
-                const unsigned int a = lim - M;
-                if (c >= 4096u) {                                 // quotient < 2^12: the approximate division is off by < 1
-                    t = (unsigned int)__fdividef((float)a, (float)c);
-                    if ((t + 1u) * c <= a) ++t;
-                    if (t * c > a) --t;
-                } else t = a / c;
-                t = min(t, (unsigned int)(nmax - k));
-                d = __int_as_float((int)(((unsigned int)E << 23) | ((M + t * c) & 0x7fffffu)));
-                k += (int)t;
-            }
-        }
-        // one real addition: it crosses the binade, or passes tau, or is one of the unusual cases above
-        if (d <= tau && k < nmax) { d = d + e; ++k; }
-    }
-    while (d <= tau && k < nmax) { d = d + e; ++k; }              // not reached in practice
+    while (d <= tau && k < nmax) { d = d + e; ++k; }
     return k;
 }
 
-// distance-field value of the ray's cell (0 when the ray is outside the volume): >= 2 means a skip is worth trying
+// skip-field byte of the ray's brick (0 when the ray is outside the volume); a skip is worth trying when either level is >= 2
 VT_DEV int dda_skip_radius(const Volume& V, const Dda& s)
 {
     if ((unsigned)s.ix >= (unsigned)V.X || (unsigned)s.iy >= (unsigned)V.Y || (unsigned)s.iz >= (unsigned)V.Z) return 0;
-    return (int)__ldg(V.dist + ((s.ix >> 3) + (s.iy >> 3) * V.CX + (s.iz >> 3) * V.CXY));
+    return (int)__ldg(V.skip + ((s.ix >> 2) + (s.iy >> 2) * V.SX + (s.iz >> 2) * V.SXY));
 }
-VT_DEV int dda_skip(const Volume& V, Dda& s, int k)      // k = dda_skip_radius >= 2; returns the number of steps skipped
+#ifndef VT_SKIP_MAX_ADD
+#define VT_SKIP_MAX_ADD 128
+#endif
+VT_DEV bool dda_skip_wanted(int v) { return v >= (2 << 2) || (v & 3) >= 2; }
+VT_DEV int dda_skip(const Volume& V, Dda& s, int v)      // v = dda_skip_radius with dda_skip_wanted(v); returns the number of steps skipped
 {
-    const int cx = s.ix >> 3, cy = s.iy >> 3, cz = s.iz >> 3;
-    const int r = (k - 1) << 3;
-    const int nx = (s.sx > 0) ? min((cx << 3) + 7 + r, V.X - 1) - s.ix : s.ix - max((cx << 3) - r, 0);   // steps that stay inside
-    const int ny = (s.sy > 0) ? min((cy << 3) + 7 + r, V.Y - 1) - s.iy : s.iy - max((cy << 3) - r, 0);
-    const int nz = (s.sz > 0) ? min((cz << 3) + 7 + r, V.Z - 1) - s.iz : s.iz - max((cz << 3) - r, 0);
-    if (min(nx, min(ny, nz)) < 4) return 0;
+    // the far field (8^3 cells) when it allows a skip at all, else the near field (4^3 bricks)
+    const int k8 = v >> 2;
+    const int shift = (k8 >= 2) ? 3 : 2, k = (k8 >= 2) ? k8 : (v & 3);
+    const int cell = (1 << shift) - 1;
+    const int cx = s.ix >> shift, cy = s.iy >> shift, cz = s.iz >> shift;
+    const int r = (k - 1) << shift;
+    // steps that stay inside, per axis; at most VT_SKIP_MAX_ADD of them are taken in one go (any smaller box is as valid: the
+    // additions of the whole warp run in lockstep, and one lane with a 127-step run would keep the others waiting)
+    const int nx = min(VT_SKIP_MAX_ADD, (s.sx > 0) ? min((cx << shift) + cell + r, V.X - 1) - s.ix : s.ix - max((cx << shift) - r, 0));
+    const int ny = min(VT_SKIP_MAX_ADD, (s.sy > 0) ? min((cy << shift) + cell + r, V.Y - 1) - s.iy : s.iy - max((cy << shift) - r, 0));
+    const int nz = min(VT_SKIP_MAX_ADD, (s.sz > 0) ? min((cz << shift) + cell + r, V.Z - 1) - s.iz : s.iz - max((cz << shift) - r, 0));
+    if (min(nx, min(ny, nz)) < 3) return 0;
     // first value at which axis a would step OUT of the box: D_a(n_a) ~ d_a + n_a e_a; stay 0.1 % below the smallest
     const float tau = gmin(s.dx + (float)nx * s.ex, gmin(s.dy + (float)ny * s.ey, s.dz + (float)nz * s.ez)) * 0.999f;
     if (!(tau > gmin(s.dx, gmin(s.dy, s.dz))) || !(tau < 3.0e38f)) return 0;

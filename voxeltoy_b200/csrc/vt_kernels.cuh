@@ -238,6 +238,34 @@ VT_GLOBAL void vt_dist_init_kernel(const unsigned long long* __restrict__ bricks
         dist[i] = solid ? 0 : (unsigned char)cap;
     }
 }
+// near field, pass 0: one thread per 4^3 brick: 0 if any in-volume voxel of the brick is set, else `cap`
+VT_GLOBAL void vt_dist4_init_kernel(const unsigned long long* __restrict__ bricks, unsigned char* __restrict__ dist,
+                                     int X, int Y, int Z, int PBX, int BXY, int BX, int BY, int BZ, int cap)
+{
+    const int n = BX * BY * BZ;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int bx = i % BX, r = i / BX, by = r % BY, bz = r / BY;
+        unsigned long long w = __ldg(bricks + ((long long)bx + (long long)by * PBX + (long long)bz * BXY));
+        bool solid = false;
+        if (w != 0ull) {
+            if (bx * 4 + 3 < X && by * 4 + 3 < Y && bz * 4 + 3 < Z) solid = true;
+            else for (int k = 0; k < 64; ++k)                         // brick straddles the boundary: ignore the sentinel bits
+                if (((w >> k) & 1ull) && bx * 4 + (k & 3) < X && by * 4 + ((k >> 2) & 3) < Y && bz * 4 + (k >> 4) < Z) { solid = true; break; }
+        }
+        dist[i] = solid ? 0 : (unsigned char)cap;
+    }
+}
+// the skip field of Volume: per brick, k8 of its 8^3 cell in bits 2..7 and k4 (<= 3) in bits 0..1
+VT_GLOBAL void vt_skip_combine_kernel(const unsigned char* __restrict__ d8, const unsigned char* __restrict__ d4, unsigned char* __restrict__ out,
+                                       int BX, int BY, int BZ, int CX, int CY)
+{
+    const int n = BX * BY * BZ;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int bx = i % BX, r = i / BX, by = r % BY, bz = r / BY;
+        const int k8 = d8[(bx >> 1) + (by >> 1) * CX + (bz >> 1) * CX * CY], k4 = d4[i];
+        out[i] = (unsigned char)((min(k8, 63) << 2) | min(k4, 3));
+    }
+}
 // Chebyshev distance transform, separable: d(c) = min over (jx, jy, jz) of max(|jx|, |jy|, |jz|) with solid(c + j)
 //   = min_jz max(|jz|, min_jy max(|jy|, min_jx max(|jx|, [0 if solid(c + j) else cap]))) -- one 1-D pass per axis.
 // axis: 0 x, 1 y, 2 z; values are capped at `cap`; cells outside the grid impose nothing.

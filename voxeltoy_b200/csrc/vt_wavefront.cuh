@@ -61,6 +61,10 @@ constexpr int kWfLiveMin = VT_WF_LIVE_MIN;
 #define VT_WF_STEP_CHUNK 16
 #endif
 constexpr int kWfStepChunk = VT_WF_STEP_CHUNK;
+#ifndef VT_WF_STEP_CHUNK_SKIP
+#define VT_WF_STEP_CHUNK_SKIP 16
+#endif
+constexpr int kWfStepChunkSkip = VT_WF_STEP_CHUNK_SKIP;   // chunk of the kernel instance with the empty-space skip (one skip attempt per chunk)
 #ifndef VT_WF_GRAB
 #define VT_WF_GRAB 128
 #endif
@@ -334,7 +338,8 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S, const int primar
     unsigned int range_next = 0, range_end = 0;     // warp-uniform
     unsigned int w = 0;                             // ray index of the lane's ray
     int status = DDA_NOHIT, guard = 0;
-    const int chunk_guard = (V.X + V.Y + V.Z) / kWfStepChunk + 8;   // belt and braces: see dda_begin on why rays always leave
+    constexpr int kChunk = (SKIP && !COUNT) ? kWfStepChunkSkip : kWfStepChunk;
+    const int chunk_guard = (V.X + V.Y + V.Z) / kChunk + 8;         // belt and braces: see dda_begin on why rays always leave
     Dda s;
     s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.steps = 0; s.bkey = -1; s.brick = 0ull;
     s.dx = s.dy = s.dz = 0.f; s.ex = s.ey = s.ez = 0.f; s.sx = s.sy = s.sz = 1;
@@ -423,7 +428,7 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S, const int primar
         for (;;) {
             if (have && status == DDA_RUNNING) {   // lanes leave the chunk through `break`: one reconvergence point per chunk, not per step
                 #pragma unroll
-                for (int k = 0; k < kWfStepChunk; ++k) {
+                for (int k = 0; k < kChunk; ++k) {
                     status = dda_step<COUNT>(V, s, tl);
                     if (status != DDA_RUNNING) break;
                 }
@@ -434,9 +439,9 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S, const int primar
                 // divergent set-up is not paid for one or two lanes while the rest of the warp idles
                 const bool running = have && status == DDA_RUNNING;
                 const int radius = running ? dda_skip_radius(V, s) : 0;
-                const unsigned m_running = __ballot_sync(full, running), m_want = __ballot_sync(full, radius >= 2);
+                const unsigned m_running = __ballot_sync(full, running), m_want = __ballot_sync(full, dda_skip_wanted(radius));
                 if (m_want != 0u && (__popc(m_want) >= kWfSkipMinLanes || 2 * __popc(m_want) >= __popc(m_running))) {
-                    if (radius >= 2) {
+                    if (dda_skip_wanted(radius)) {
                         const int skipped = dda_skip(V, s, radius);
 #ifdef VT_SKIP_STATS
                         dbg_calls += 1; dbg_ok += skipped > 0; dbg_steps += skipped;

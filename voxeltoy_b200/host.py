@@ -55,6 +55,7 @@ _SIG = {
     "vth_tool_create": (P, [P, C.c_int]), "vth_tool_destroy": (None, [P]),
     "vth_tool_mouse": (C.c_int, [P] + [C.c_int] * 7),
     "vth_vox_load": (P, [C.c_char_p]), "vth_vox_error": (C.c_char_p, [P]),
+    "vth_vox_load_rules": (P, [C.c_char_p, f32p, C.c_int]), "vth_renderer_set_vox_palette_rules": (None, [P, f32p, C.c_int]),
     "vth_vox_dims": (None, [P, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "vth_vox_copy": (None, [P, i32p, f32p, i32p]), "vth_vox_free": (None, [P]),
     "vth_obj_load": (P, [C.c_char_p]), "vth_obj_dims": (None, [P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
@@ -114,10 +115,25 @@ def plain_path(path):
 
 
 # ---- loaders ------------------------------------------------------------------------------------------------
-def load_vox(path):
-    """MagicaVoxelLoader::load. Returns dict(res, grid, materials, emissive)."""
+MT_LAMBERT, MT_METAL, MT_PLASTIC = 0, 1, 2
+
+
+def _rules_array(rules):
+    """[(colour index, material type, (er, eg, eb), roughness), ...] -> the flat float array of the C wrappers."""
+    a = np.zeros((len(rules), 6), np.float32)
+    for i, (ci, mt, em, rough) in enumerate(rules):
+        a[i] = (ci, mt, em[0], em[1], em[2], rough)
+    return a
+
+
+def load_vox(path, palette_rules=None):
+    """MagicaVoxelLoader::load (with the new-build palette rules when given). Returns dict(res, grid, materials, emissive)."""
     L = lib()
-    h = L.vth_vox_load(plain_path(path).encode())
+    if palette_rules:
+        ra = _rules_array(palette_rules)
+        h = L.vth_vox_load_rules(plain_path(path).encode(), _fp(ra), len(palette_rules))
+    else:
+        h = L.vth_vox_load(plain_path(path).encode())
     try:
         res = (C.c_int * 3)(); nm = C.c_size_t(); ne = C.c_size_t()
         L.vth_vox_dims(h, res, C.byref(nm), C.byref(ne))
@@ -281,6 +297,10 @@ class Renderer:
 
     def reloadShaders(self, path=""):
         self._L.vth_renderer_reload_shaders(self._h, path.encode())
+
+    def setVoxPaletteRules(self, rules):
+        ra = _rules_array(rules or [])
+        self._L.vth_renderer_set_vox_palette_rules(self._h, _fp(ra) if len(ra) else None, len(ra))
 
     def loadVoxFile(self, path):
         self._L.vth_renderer_load_vox_file(self._h, plain_path(path).encode())

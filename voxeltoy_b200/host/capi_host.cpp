@@ -132,6 +132,27 @@ void vth_renderer_resolution(void* r, int* w, int* h) { *w = R(r).renderSettings
 void vth_widget_size(void* w, int* width, int* height) { *width = static_cast<HeadlessWidget*>(w)->width(); *height = static_cast<HeadlessWidget*>(w)->height(); }
 
 // ---- loaders -------------------------------------------------------------------------------------------------------------
+// palette rules: n records of (colour index, material type, emission r g b, roughness) as 6 floats each
+static std::vector<MagicaVoxelLoader::PaletteRule> palette_rules(const float* rules, int n)
+{
+    std::vector<MagicaVoxelLoader::PaletteRule> out;
+    for (int i = 0; rules && i < n; ++i) {
+        MagicaVoxelLoader::PaletteRule r;
+        r.colorIndex = (int)rules[6 * i]; r.type = (Material::MaterialType)(int)rules[6 * i + 1];
+        r.emission = V3f(rules[6 * i + 2], rules[6 * i + 3], rules[6 * i + 4]); r.roughness = rules[6 * i + 5];
+        out.push_back(r);
+    }
+    return out;
+}
+void vth_renderer_set_vox_palette_rules(void* h, const float* rules, int n) { R(h).setVoxPaletteRules(palette_rules(rules, n)); }
+void* vth_vox_load_rules(const char* path, const float* rules, int n)
+{
+    VoxResult* r = new VoxResult();
+    MagicaVoxelLoader loader;
+    loader.setPaletteRules(palette_rules(rules, n));
+    if (!loader.load(path, r->grid, r->materials, r->emissive, r->res)) { r->error = loader.m_error; r->res = V3i(0); }
+    return r;
+}
 void* vth_vox_load(const char* path)
 {
     VoxResult* r = new VoxResult();

@@ -4,6 +4,8 @@
 // tinyobjloader the reference links (thirdParty/tinyobjloader/tiny_obj_loader.cc) -- restated, not copied.
 #include "vt_host.h"
 
+#include <algorithm>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -126,7 +128,10 @@ bool MagicaVoxelLoader::loadFromMemory(const unsigned char* bytes, size_t n, std
     if (version != 150) { m_error = "version does not match"; return false; }
     rd.i32(id); rd.i32(contentSize); rd.i32(childrenSize);
     if (id != kMAIN) { m_error = "main chunk is not found"; return false; }
-    const size_t mainEnd = rd.pos + (size_t)contentSize + (size_t)childrenSize;
+    // chunk sizes come from the file: negative or oversized values must not move the cursor backwards or past the data
+    // (the reference trusts them, magicaVoxel.cpp:150-206)
+    if (contentSize < 0 || childrenSize < 0 || (size_t)contentSize > n - rd.pos) { m_error = "corrupt chunk"; return false; }
+    const size_t mainEnd = std::min(n, rd.pos + (size_t)contentSize + (size_t)childrenSize);
     rd.pos += contentSize;
 
     int sx = 0, sy = 0, sz = 0, numVoxels = 0;
@@ -134,8 +139,11 @@ bool MagicaVoxelLoader::loadFromMemory(const unsigned char* bytes, size_t n, std
     unsigned char palette[256][4];
     bool customPalette = false;
     while (rd.pos < mainEnd && rd.pos < n) {
+        if (rd.pos + 12 > mainEnd) break;                                   // trailing bytes that cannot hold a chunk header
         rd.i32(id); rd.i32(contentSize); rd.i32(childrenSize);
+        if (contentSize < 0 || childrenSize < 0) { m_error = "corrupt chunk"; return false; }
         const size_t end = rd.pos + (size_t)contentSize + (size_t)childrenSize;
+        if (end > mainEnd) { m_error = "corrupt chunk"; return false; }
         if (id == kSIZE) { int32_t a, b, c; rd.i32(a); rd.i32(b); rd.i32(c); sx = a; sy = b; sz = c; }
         else if (id == kXYZI) {
             int32_t cnt; rd.i32(cnt);
@@ -167,7 +175,13 @@ bool MagicaVoxelLoader::loadFromMemory(const unsigned char* bytes, size_t n, std
         const size_t cell = (size_t)v[0] + (size_t)v[2] * voxelResolution.x + (size_t)v[1] * voxelResolution.x * voxelResolution.y;
         if (offsetOfColour[ci] < 0) {                           // first use of this colour: one Lambert record (:300-318)
             offsetOfColour[ci] = (int32_t)materialData.size();
-            generateMaterialLambert(V3f(0, 0, 0), V3f((float)palette[ci][0] / 255, (float)palette[ci][1] / 255, (float)palette[ci][2] / 255), materialData);
+            const V3f colour((float)palette[ci][0] / 255, (float)palette[ci][1] / 255, (float)palette[ci][2] / 255);
+            const PaletteRule* rule = NULL;
+            for (size_t r = 0; r < m_rules.size(); ++r) if (m_rules[r].colorIndex == ci) rule = &m_rules[r];
+            if (!rule) generateMaterialLambert(V3f(0, 0, 0), colour, materialData);
+            else if (rule->type == Material::MT_METAL) generateMaterialMetal(rule->emission, colour, rule->roughness, materialData);
+            else if (rule->type == Material::MT_PLASTIC) generateMaterialPlastic(rule->emission, colour, rule->roughness, materialData);
+            else generateMaterialLambert(rule->emission, colour, materialData);
         }
         voxelMaterials[cell] = offsetOfColour[ci];
     }

@@ -410,6 +410,7 @@ void Renderer::loadVoxFile(const std::string& file)                             
     std::vector<int32_t> voxelMaterials, emissive;
     std::vector<float> materialData;
     MagicaVoxelLoader loader;
+    loader.setPaletteRules(m_voxPaletteRules);
     V3i res;
     if (!loader.load(file, voxelMaterials, materialData, emissive, res)) { log("[error] MV_VoxelModel :: " + loader.m_error); return; }
     setVoxelData(res, voxelMaterials, materialData, emissive);

@@ -99,11 +99,19 @@ public:
 };
 class MagicaVoxelLoader : public VoxLoader {
 public:
+    // New-build extension: the .vox format carries colours only, and the reference can therefore generate
+    // nothing but Lambert records (magicaVoxel.cpp:306-317). A palette rule turns one colour index into a Lambert / Metal /
+    // Plastic record with emission and roughness; the colour stays the palette's. Without rules the loader is the reference's.
+    struct PaletteRule { int colorIndex; Material::MaterialType type; vtm::V3f emission; float roughness; };
+    void setPaletteRules(const std::vector<PaletteRule>& rules) { m_rules = rules; }
+    const std::vector<PaletteRule>& paletteRules() const { return m_rules; }
     bool load(const std::string& filePath, std::vector<int32_t>& voxelMaterials, std::vector<float>& materialData,
               std::vector<int32_t>& emissiveVoxelIndices, vtm::V3i& voxelResolution) override;
     bool loadFromMemory(const unsigned char* bytes, size_t n, std::vector<int32_t>& voxelMaterials, std::vector<float>& materialData,
                         std::vector<int32_t>& emissiveVoxelIndices, vtm::V3i& voxelResolution);
     std::string m_error;
+private:
+    std::vector<PaletteRule> m_rules;
 };
 
 // ---- mesh/mesh.h, mesh/meshLoader.h:8-15 ------------------------------------------------------------------
@@ -309,6 +317,7 @@ public:
     void loadMesh(const std::string& file);
     void loadMeshAtResolution(const std::string& file, int resolution);   // new-build: the reference hard-codes 64 (import.cpp:75)
     void loadVoxFile(const std::string& file);
+    void setVoxPaletteRules(const std::vector<MagicaVoxelLoader::PaletteRule>& rules) { m_voxPaletteRules = rules; }   // new-build: applied by loadVoxFile
     // new-build: the public twin of createVoxelDataTexture for scenes that are not files
     void setVoxelData(const vtm::V3i& resolution, const std::vector<int32_t>& voxelMaterials, const std::vector<float>& materialData,
                       const std::vector<int32_t>& emissiveVoxelIndices);
@@ -361,6 +370,7 @@ private:
     Logger* m_logger;
     RendererService* m_services[SERVICE_TOTAL];
     std::vector<float> m_materialData;          // host mirror for getMaterials (the reference reads the texture back)
+    std::vector<MagicaVoxelLoader::PaletteRule> m_voxPaletteRules;
     vtm::M44f m_mvm, m_invMvm, m_pm, m_invPm;
 };
 
