@@ -184,6 +184,10 @@ int vt_voxelize(vt_ctx* ctx, const float* xyz, size_t n_verts, const uint32_t* i
 /* replace material offsets of solid voxels by rule(x,y,z): new-build extension used by BASELINE config 3. */
 int vt_volume_assign_materials(vt_ctx* ctx, const int32_t* offsets_table, int n_table, int rule);
 /* elapsed GPU milliseconds of the last vt_voxelize (clear + scatter + derive), cudaEvent-timed */
+/* THICKNESS of voxelize.gs:15-19: THIN (default, what the reference compiles: adjacent voxels connected at least by vertices)
+ * or FAT (the conservative variant in the same shader text: adjacent voxels share at least a face) */
+enum { VT_VOXELIZE_THIN = 0, VT_VOXELIZE_FAT = 1 };
+int vt_set_voxelize_thickness(vt_ctx* ctx, int thickness);
 int vt_get_last_voxelize_ms(vt_ctx* ctx, float* ms);
 /* the same call's device time including what the pipeline needs next: the material-id grid made valid (cleared to "empty", the
  * solid voxels filled) and the renderer's empty-space distance field */

@@ -39,6 +39,7 @@ def lib():
         L.vtref_remove_voxel.argtypes = [i32p, i32p]
         L.vtref_voxelize.argtypes = [f32p, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t, f32p, C.c_int, C.c_int, C.c_int,
                                      C.POINTER(C.c_uint8), C.c_int]
+        L.vtref_voxelize_fat.argtypes = L.vtref_voxelize.argtypes
         _LIB = L
     return _LIB
 
@@ -104,11 +105,38 @@ def remove_voxel(sel_index):
     return coord
 
 
-def voxelize(verts, idx, M, res, n_threads=None):
+def voxelize(verts, idx, M, res, n_threads=None, fat=False):
     verts = np.ascontiguousarray(verts, np.float32); idx = np.ascontiguousarray(idx, np.uint32)
     M = np.ascontiguousarray(M, np.float32)
     X, Y, Z = [int(v) for v in res]
     occ = np.zeros(X * Y * Z, np.uint8)
-    lib().vtref_voxelize(_fp(verts), verts.size // 3, idx.ctypes.data_as(C.POINTER(C.c_uint32)), idx.size, _fp(M), X, Y, Z,
-                         occ.ctypes.data_as(C.POINTER(C.c_uint8)), int(n_threads or os.cpu_count() or 1))
+    fn = lib().vtref_voxelize_fat if fat else lib().vtref_voxelize
+    fn(_fp(verts), verts.size // 3, idx.ctypes.data_as(C.POINTER(C.c_uint32)), idx.size, _fp(M), X, Y, Z,
+       occ.ctypes.data_as(C.POINTER(C.c_uint8)), int(n_threads or os.cpu_count() or 1))
     return occ
+
+
+# ---- the reference's OBJ reader (thirdParty/tinyobjloader/tiny_obj_loader.cc + the merge of mesh/meshLoader.cpp:27-64) ----
+_OBJ_PATH = os.path.join(_HERE, "_ref", "libvt_ref_obj.so")
+_OBJ_LIB = None
+
+
+def obj_available():
+    return os.path.exists(_OBJ_PATH)
+
+
+def load_obj(path):
+    """MeshLoader::loadFromOBJ through the reference's own tinyobjloader: (verts (n, 3) float32, indices uint32)."""
+    global _OBJ_LIB
+    if _OBJ_LIB is None:
+        L = C.CDLL(_OBJ_PATH)
+        L.vtref_load_obj.argtypes = [C.c_char_p, C.POINTER(f32p), C.POINTER(C.c_size_t), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_size_t)]
+        L.vtref_obj_free.argtypes = [C.c_void_p]
+        _OBJ_LIB = L
+    v = f32p(); nv = C.c_size_t(); i = C.POINTER(C.c_uint32)(); ni = C.c_size_t()
+    if _OBJ_LIB.vtref_load_obj(path.encode(), C.byref(v), C.byref(nv), C.byref(i), C.byref(ni)) != 0:
+        raise IOError("tinyobj::LoadObj failed on " + path)
+    verts = np.ctypeslib.as_array(v, shape=(max(nv.value, 1),))[:nv.value].copy().reshape(-1, 3)
+    idx = np.ctypeslib.as_array(i, shape=(max(ni.value, 1),))[:ni.value].copy()
+    _OBJ_LIB.vtref_obj_free(v); _OBJ_LIB.vtref_obj_free(i)
+    return verts, idx

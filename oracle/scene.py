@@ -163,31 +163,55 @@ def prune_interior_emissive(grid, res, emissive):
 # ---------------------------------------------------------------------------
 
 def load_obj(path_or_bytes):
+    """MeshLoader::loadFromOBJ over tinyobj::LoadObj (tiny_obj_loader.cc:489-716, pinned against the reference's own copy by
+    tests/test_oracle_vs_reference.py): faces are gathered into a face group; `g` / `o` (and the end of the file) export the
+    group as one shape -- polygons as triangle fans, vertices in first-use order with a cache that lives for ONE shape
+    (:226-275, the cache is passed by value) -- and `usemtl` DROPS the faces gathered so far (:617-623). meshLoader.cpp:40-63
+    then concatenates the shapes, offsetting their indices."""
     data = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray)) else read_bytes(path_or_bytes)
     pos_in = []
+    n_vt = n_vn = 0
     verts, idx = [], []
-    cache = {}
+    group = []
+
+    def fix(i, n):                                   # fixIndex: 1-based, negative = relative to the end, 0 -> 0
+        return i - 1 if i > 0 else (0 if i == 0 else n + i)
+
+    def export():
+        cache = {}
+        base = len(verts)
+        for face in group:
+            for k in range(2, len(face)):
+                for key in (face[0], face[k - 1], face[k]):
+                    if key not in cache:
+                        cache[key] = len(verts) - base
+                        verts.append(pos_in[key[0]])
+                    idx.append(base + cache[key])
+        del group[:]
+
     for line in data.decode("latin-1").splitlines():
-        t = line.strip()
+        t = line.strip(" \t\r")
         if t.startswith("v ") or t.startswith("v\t"):
             p = t.split()
             pos_in.append((f32(float(p[1])), f32(float(p[2])), f32(float(p[3]))))
+        elif t.startswith("vn ") or t.startswith("vn\t"):
+            n_vn += 1
+        elif t.startswith("vt ") or t.startswith("vt\t"):
+            n_vt += 1
         elif t.startswith("f ") or t.startswith("f\t"):
             face = []
             for tok in t.split()[1:]:
                 parts = tok.split("/")
-                vi = int(parts[0]); vi = vi - 1 if vi > 0 else len(pos_in) + vi
-                vt = int(parts[1]) if len(parts) > 1 and parts[1] else None
-                vn = int(parts[2]) if len(parts) > 2 and parts[2] else None
+                vi = fix(int(parts[0]), len(pos_in))
+                vt = fix(int(parts[1]), n_vt) if len(parts) > 1 and parts[1] else -1
+                vn = fix(int(parts[2]), n_vn) if len(parts) > 2 and parts[2] else -1
                 face.append((vi, vt, vn))
-            for k in range(2, len(face)):
-                for key in (face[0], face[k - 1], face[k]):
-                    if key not in cache:
-                        cache[key] = len(verts)
-                        verts.append(pos_in[key[0]])
-                    idx.append(cache[key])
-        elif t.startswith("g ") or t.startswith("o "):
-            pass  # groups start new shapes; meshLoader merges them again (single index space per shape)
+            group.append(face)
+        elif t.startswith("usemtl ") or t.startswith("usemtl\t"):
+            del group[:]
+        elif t[:2] in ("g ", "g\t", "o ", "o\t"):
+            export()
+    export()
     return np.array(verts, np.float32).reshape(-1, 3), np.array(idx, np.uint32)
 
 

@@ -1,7 +1,10 @@
 #!/usr/bin/env python3
 """TEST INFRASTRUCTURE -- turns one of the reference's GLSL programs into a C++ struct, on stdout.
 
-    glsl2cpp.py <shader dir> <root shader file> <StructName> [-DNAME ...]
+    glsl2cpp.py <shader dir> <root shader file> <StructName> [-DNAME ...] [--set NAME=VALUE ...]
+
+--set rewrites the value of a `#define NAME <value>` line of the shader text itself: the edit a maintainer of the reference makes
+to pick a compile-time variant the text already contains (voxelize.gs:15-19: `#define THICKNESS THIN` / FAT).
 
 The shader TEXT is read from the reference tree where it lies (never copied into the repo). Steps:
   1. the preprocessor defines the reference passes as source string 0 (renderer.cpp:227, servicePicking.cpp:21),
@@ -91,8 +94,13 @@ def rewrite(code):
 def main():
     base, root, name = sys.argv[1], sys.argv[2], sys.argv[3]
     defines = [a[2:] for a in sys.argv[4:] if a.startswith("-D")]
+    sets = [sys.argv[i + 1].split("=", 1) for i in range(4, len(sys.argv) - 1) if sys.argv[i] == "--set"]
     with open(os.path.join(base, root)) as fh:
         code = fh.read()
+    for nm, val in sets:
+        code, n = re.subn(r"^(\s*#\s*define\s+%s)\s+\w+[^\n]*" % re.escape(nm), r"\1 %s" % val, code, flags=re.M)
+        if n != 1:
+            raise SystemExit("--set %s: expected exactly one #define line, found %d" % (nm, n))
     code = "".join("#define %s\n" % d for d in defines) + code
     code = splice_includes(code, base if base.endswith("/") else base + "/")
     body = rewrite(code)

@@ -17,6 +17,7 @@ namespace glsl {
 #include "gen_RemoveVoxelVS.inc"
 #include "gen_VoxelizeVS.inc"
 #include "gen_VoxelizeGS.inc"
+#include "gen_VoxelizeGSFat.inc"
 
 static mat4 from_row_major(const float* m)      // glUniformMatrix4fv(..., GL_TRUE, m): M[c][r] = m[4r + c]
 {
@@ -181,8 +182,10 @@ void vtref_remove_voxel(const int32_t sel_index[4], int32_t coord[3])
 }
 
 // K5: shared/voxelize.vs per vertex + shared/voxelize.gs per triangle (Mesh::draw = glDrawElements(GL_TRIANGLES), mesh.cpp:55-59)
-void vtref_voxelize(const float* xyz, size_t n_verts, const uint32_t* idx, size_t n_idx, const float M[16],
-                    int X, int Y, int Z, uint8_t* occupancy, int n_threads)
+} // extern "C"
+template <class GS>
+static void run_voxelizer(const float* xyz, size_t n_verts, const uint32_t* idx, size_t n_idx, const float M[16],
+                          int X, int Y, int Z, uint8_t* occupancy, int n_threads)
 {
     std::vector<vec3> vs(n_verts);
     {
@@ -198,7 +201,7 @@ void vtref_voxelize(const float* xyz, size_t n_verts, const uint32_t* idx, size_
     const long n_tris = (long)(n_idx / 3);
     #pragma omp parallel num_threads(n_threads > 0 ? n_threads : omp_get_max_threads())
     {
-        VoxelizeGS g;
+        GS g;
         g.voxelResolution = ivec3(X, Y, Z);
         g.voxelOccupancy.occ = occupancy; g.voxelOccupancy.X = X; g.voxelOccupancy.Y = Y; g.voxelOccupancy.Z = Z;
         #pragma omp for schedule(dynamic, 16)
@@ -207,6 +210,18 @@ void vtref_voxelize(const float* xyz, size_t n_verts, const uint32_t* idx, size_
             g.main();
         }
     }
+}
+extern "C" {
+void vtref_voxelize(const float* xyz, size_t n_verts, const uint32_t* idx, size_t n_idx, const float M[16],
+                    int X, int Y, int Z, uint8_t* occupancy, int n_threads)
+{
+    run_voxelizer<VoxelizeGS>(xyz, n_verts, idx, n_idx, M, X, Y, Z, occupancy, n_threads);
+}
+// the FAT variant of the same shader text (voxelize.gs:15-19 with `#define THICKNESS FAT`)
+void vtref_voxelize_fat(const float* xyz, size_t n_verts, const uint32_t* idx, size_t n_idx, const float M[16],
+                        int X, int Y, int Z, uint8_t* occupancy, int n_threads)
+{
+    run_voxelizer<VoxelizeGSFat>(xyz, n_verts, idx, n_idx, M, X, Y, Z, occupancy, n_threads);
 }
 
 } // extern "C"

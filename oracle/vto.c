@@ -1024,7 +1024,13 @@ static inline float edge_d(v2 n, float va, float vb)
 }
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-static void voxelize_tri(v3 v0, v3 v1, v3 v2_, int X, int Y, int Z, uint8_t* occ)
+/* voxelize.gs:151-163 (FAT): -dot(n, v) + max(0, n.x) + max(0, n.y) */
+static inline float edge_d_fat(v2 n, float va, float vb)
+{
+    return (-v2dot(n, V2(va, vb)) + g_max(0.0f, n.x)) + g_max(0.0f, n.y);
+}
+
+static void voxelize_tri(v3 v0, v3 v1, v3 v2_, int X, int Y, int Z, uint8_t* occ, int fat)
 {
     /* swizzleTri, voxelize.gs:55-109 */
     v3 n = v3cross(v3sub(v1, v0), v3sub(v2_, v1));
@@ -1033,7 +1039,7 @@ static void voxelize_tri(v3 v0, v3 v1, v3 v2_, int X, int Y, int Z, uint8_t* occ
     int lo[3], hi[3], px, py, pz;
     v3 e0, e1, e2, nP, mn, mx;
     v2 n0xy, n1xy, n2xy, n0yz, n1yz, n2yz, n0zx, n1zx, n2zx;
-    float d0xy, d1xy, d2xy, d0yz, d1yz, d2yz, d0zx, d1zx, d2zx, dTri, dThin, nzInv;
+    float d0xy, d1xy, d2xy, d0yz, d1yz, d2yz, d0zx, d1zx, d2zx, dTri, dThin, dFatMin, dFatMax, nzInv;
     if (an.x >= an.y && an.x >= an.z) {
         axis = 0;
         v0 = V3(v0.y, v0.z, v0.x); v1 = V3(v1.y, v1.z, v1.x); v2_ = V3(v2_.y, v2_.z, v2_.x); n = V3(n.y, n.z, n.x);
@@ -1057,9 +1063,16 @@ static void voxelize_tri(v3 v0, v3 v1, v3 v2_, int X, int Y, int Z, uint8_t* occ
     d0xy = edge_d(n0xy, v0.x, v0.y); d1xy = edge_d(n1xy, v1.x, v1.y); d2xy = edge_d(n2xy, v2_.x, v2_.y);
     d0yz = edge_d(n0yz, v0.y, v0.z); d1yz = edge_d(n1yz, v1.y, v1.z); d2yz = edge_d(n2yz, v2_.y, v2_.z);
     d0zx = edge_d(n0zx, v0.z, v0.x); d1zx = edge_d(n1zx, v1.z, v1.x); d2zx = edge_d(n2zx, v2_.z, v2_.x);
+    if (fat) {                                                              /* voxelize.gs:151-163 */
+        d0xy = edge_d_fat(n0xy, v0.x, v0.y); d1xy = edge_d_fat(n1xy, v1.x, v1.y); d2xy = edge_d_fat(n2xy, v2_.x, v2_.y);
+        d0yz = edge_d_fat(n0yz, v0.y, v0.z); d1yz = edge_d_fat(n1yz, v1.y, v1.z); d2yz = edge_d_fat(n2yz, v2_.y, v2_.z);
+        d0zx = edge_d_fat(n0zx, v0.z, v0.x); d1zx = edge_d_fat(n1zx, v1.z, v1.x); d2zx = edge_d_fat(n2zx, v2_.z, v2_.x);
+    }
     nP = (n.z < 0.0f) ? v3neg(n) : n;
     dTri = v3dot(nP, v0);
     dThin = dTri - v2dot(V2(nP.x, nP.y), V2(0.5f, 0.5f));
+    dFatMin = (dTri - g_max(nP.x, 0.0f)) - g_max(nP.y, 0.0f);               /* :170-171 */
+    dFatMax = (dTri - g_min(nP.x, 0.0f)) - g_min(nP.y, 0.0f);
     nzInv = 1.0f / nP.z;
 
     for (px = lo[0]; px < hi[0]; px++) {
@@ -1068,10 +1081,11 @@ static void voxelize_tri(v3 v0, v3 v1, v3 v2_, int X, int Y, int Z, uint8_t* occ
             float a0 = d0xy + v2dot(n0xy, pxy), a1 = d1xy + v2dot(n1xy, pxy), a2 = d2xy + v2dot(n2xy, pxy);
             if ((a0 >= 0.0f) && (a1 >= 0.0f) && (a2 >= 0.0f)) {
                 float dot_n_p = v2dot(V2(nP.x, nP.y), pxy);
-                float zInt = (-dot_n_p + dThin) * nzInv;
-                float zf = floorf(zInt), zc = ceilf(zInt);
-                int zMin = g_f2i(zf) - (zf == zInt ? 1 : 0);
-                int zMax = g_f2i(zc) + (zc == zInt ? 1 : 0);
+                float zMinInt = fat ? (-dot_n_p + dFatMin) * nzInv : (-dot_n_p + dThin) * nzInv;     /* :195-201 */
+                float zMaxInt = fat ? (-dot_n_p + dFatMax) * nzInv : zMinInt;
+                float zf = floorf(zMinInt), zc = ceilf(zMaxInt);
+                int zMin = g_f2i(zf) - (zf == zMinInt ? 1 : 0);
+                int zMax = g_f2i(zc) + (zc == zMaxInt ? 1 : 0);
                 if (zMin < lo[2]) zMin = lo[2];
                 if (zMax > hi[2]) zMax = hi[2];
                 for (pz = zMin; pz < zMax; pz++) {
@@ -1095,8 +1109,8 @@ static void voxelize_tri(v3 v0, v3 v1, v3 v2_, int X, int Y, int Z, uint8_t* occ
     (void)clampi;
 }
 
-void vto_voxelize(const float* xyz, size_t n_verts, const uint32_t* idx, size_t n_idx,
-                  const float M[16], int X, int Y, int Z, uint8_t* occ, int n_threads)
+static void voxelize_mesh(const float* xyz, size_t n_verts, const uint32_t* idx, size_t n_idx,
+                          const float M[16], int X, int Y, int Z, uint8_t* occ, int n_threads, int fat)
 {
     long t, ntri = (long)(n_idx / 3);
     v3* vs = (v3*)malloc(sizeof(v3) * (n_verts ? n_verts : 1));
@@ -1110,8 +1124,19 @@ void vto_voxelize(const float* xyz, size_t n_verts, const uint32_t* idx, size_t 
     /* all writers store the same value: the benign race of cpuVoxelizer.cpp:99-108 */
 #pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads)
     for (t = 0; t < ntri; t++)
-        voxelize_tri(vs[idx[3 * t]], vs[idx[3 * t + 1]], vs[idx[3 * t + 2]], X, Y, Z, occ);
+        voxelize_tri(vs[idx[3 * t]], vs[idx[3 * t + 1]], vs[idx[3 * t + 2]], X, Y, Z, occ, fat);
     free(vs);
+}
+void vto_voxelize(const float* xyz, size_t n_verts, const uint32_t* idx, size_t n_idx,
+                  const float M[16], int X, int Y, int Z, uint8_t* occ, int n_threads)
+{
+    voxelize_mesh(xyz, n_verts, idx, n_idx, M, X, Y, Z, occ, n_threads, 0);
+}
+/* the FAT variant (voxelize.gs:15-19, `#define THICKNESS FAT`: adjacent voxels share at least a face) */
+void vto_voxelize_fat(const float* xyz, size_t n_verts, const uint32_t* idx, size_t n_idx,
+                      const float M[16], int X, int Y, int Z, uint8_t* occ, int n_threads)
+{
+    voxelize_mesh(xyz, n_verts, idx, n_idx, M, X, Y, Z, occ, n_threads, 1);
 }
 
 /* ------------------------------------------------------------------------- */

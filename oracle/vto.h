@@ -103,6 +103,9 @@ void vto_accumulate(float* avg, const float* sample, int n, size_t count);
 void vto_voxelize(const float* xyz, size_t n_verts, const uint32_t* idx, size_t n_idx,
                   const float M[16], int X, int Y, int Z, uint8_t* occupancy, int n_threads);
 
+void vto_voxelize_fat(const float* xyz, size_t n_verts, const uint32_t* idx, size_t n_idx,
+                      const float M[16], int X, int Y, int Z, uint8_t* occupancy, int n_threads);
+
 /* K6: editVoxels/selectVoxel.vs; viewport = (x,y,w,h). index[4], normal[4] out. */
 void vto_pick(const vto_scene* s, const float viewport[4], float near_z, float px, float py,
               int32_t index[4], float normal[4]);

@@ -64,6 +64,7 @@ def lib():
     L.vto_accumulate.argtypes = [f32p, f32p, C.c_int, C.c_size_t]
     L.vto_voxelize.argtypes = [f32p, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t, f32p,
                                C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_int]
+    L.vto_voxelize_fat.argtypes = L.vto_voxelize.argtypes
     L.vto_pick.argtypes = [C.POINTER(Scene), f32p, C.c_float, C.c_float, C.c_float, i32p, f32p]
     L.vto_pick_focal.argtypes = [C.POINTER(Scene), f32p, C.c_float, C.c_float]
     L.vto_pick_focal.restype = C.c_float
@@ -224,14 +225,14 @@ def render_average(scene, n_passes, first=0, n_threads=None):
     return avg
 
 
-def voxelize(verts, idx, M, res, n_threads=None):
+def voxelize(verts, idx, M, res, n_threads=None, fat=False):
     n_threads = n_threads or os.cpu_count() or 1
     verts = np.ascontiguousarray(verts, np.float32); idx = np.ascontiguousarray(idx, np.uint32)
     M = np.ascontiguousarray(M, np.float32)
     X, Y, Z = [int(v) for v in res]
     occ = np.zeros(X * Y * Z, np.uint8)
-    lib().vto_voxelize(_fp(verts), verts.size // 3, idx.ctypes.data_as(C.POINTER(C.c_uint32)), idx.size,
-                       _fp(M), X, Y, Z, occ.ctypes.data_as(C.POINTER(C.c_uint8)), n_threads)
+    (lib().vto_voxelize_fat if fat else lib().vto_voxelize)(_fp(verts), verts.size // 3, idx.ctypes.data_as(C.POINTER(C.c_uint32)), idx.size,
+                                                            _fp(M), X, Y, Z, occ.ctypes.data_as(C.POINTER(C.c_uint8)), n_threads)
     return occ
 
 

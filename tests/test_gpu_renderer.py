@@ -153,3 +153,52 @@ def test_uninitialized_renderer_is_inert():
     r.resetRender()
     assert r.numberSamples() == 0
     r.close()
+
+
+def test_material_authoring_round_trip(renderer, tmp_path):
+    """.vox palette rules -> Metal / Plastic / emissive records -> getMaterials (renderer.cpp:1142-1203) ->
+    updateMaterialColor / updateMaterialValue (:1205-1235) -> the render follows, bit for bit against the oracle fed with the same
+    edited material array."""
+    import struct
+    import voxeltoy_b200 as vt
+    rng = np.random.RandomState(6)
+    n = 24
+    vox = [(x, y, 0, 3) for x in range(n) for y in range(n)]                            # a floor (MagicaVoxel z is up)
+    for _ in range(30):
+        c = rng.randint(2, n - 4, size=2); h = int(rng.randint(2, 8)); ci = int(rng.choice([9, 17, 40]))
+        vox += [(int(c[0]) + dx, int(c[1]) + dy, z, ci) for dx in range(2) for dy in range(2) for z in range(1, h)]
+    xyzi = struct.pack("<i", len(vox)) + b"".join(struct.pack("<4B", *v) for v in vox)
+    chunks = b"SIZE" + struct.pack("<ii", 12, 0) + struct.pack("<iii", n, n, 10) + b"XYZI" + struct.pack("<ii", len(xyzi), 0) + xyzi
+    path = str(tmp_path / "authored.vox")
+    with open(path, "wb") as f:
+        f.write(b"VOX " + struct.pack("<i", 150) + b"MAIN" + struct.pack("<ii", 0, len(chunks)) + chunks)
+    rules = [(9, vt.host.MT_METAL, (0.0, 0.0, 0.0), 120.0), (17, vt.host.MT_LAMBERT, (4.0, 3.0, 2.0), 0.0), (40, vt.host.MT_PLASTIC, (0.0, 0.0, 0.0), 35.0)]
+    r = renderer
+    r.resizeFrame(160, 120)
+    r.setVoxPaletteRules(rules)
+    r.loadVoxFile(path)
+    r.setVoxPaletteRules([])
+    r.setRenderSettings(maxBounces=3)
+    ref = oscene.load_vox(path, palette_rules=rules)
+    ctx = r.context()
+    assert np.array_equal(ctx.read_volume(), ref["grid"])
+    mats = r.getMaterials()                                                        # [(type, offset)] in storage order
+    assert sorted(t for t, _ in mats) == [0, 0, 1, 2]
+    assert [o for _, o in mats] == sorted(set(int(v) for v in ref["grid"][ref["grid"] >= 0]))
+    metal = [o for t, o in mats if t == 1][0]; plastic = [o for t, o in mats if t == 2][0]; lamb = [o for t, o in mats if t == 0][0]
+    # the edits the reference's material panel makes (ui/mainwindow.cpp:155-250): reflectance colour, roughness, emission
+    r.updateMaterialColor(metal + 4, [0.95, 0.64, 0.54])
+    r.updateMaterialValue(metal + 7, 30.0)
+    r.updateMaterialValue(plastic + 7, 400.0)
+    r.updateMaterialColor(lamb + 1, [0.0, 0.25, 0.0])
+    m2 = ref["materials"].copy()
+    m2[metal + 4: metal + 7] = [0.95, 0.64, 0.54]; m2[metal + 7] = 30.0; m2[plastic + 7] = 400.0; m2[lamb + 1: lamb + 4] = [0.0, 0.25, 0.0]
+    assert np.array_equal(ctx.read_materials(m2.size), m2)
+    r.resetRender()
+    ctx.set_selection([-1, -1, -1, 0], [1, 0, 0, 0])
+    r.renderPasses(2)
+    em = oscene.prune_interior_emissive(ref["grid"], ref["res"], ref["emissive"])
+    d = _oracle_frame(r, dict(res=ref["res"], grid=ref["grid"], materials=m2, emissive=em), 3, sel=(-1, -1, -1))
+    want = vto.render_average(vto.make_scene(d), 2)
+    got = r.readAverage()
+    assert util.same_bits(got, want).all(), "%d floats differ" % int((~util.same_bits(got, want)).sum())

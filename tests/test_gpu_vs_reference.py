@@ -60,3 +60,24 @@ def test_voxelizer_and_services_match_reference_glsl(vt_ctx):
         assert np.array_equal(gi, ri) and util.same_bits(gn, rn).all()
         vt_ctx.pick_focal(px, py)
         assert np.float32(vt_ctx.get_focal_distance()).view(np.uint32) == np.float32(ref.pick_focal(s, px, py)).view(np.uint32)
+
+
+def test_fat_voxelizer_matches_reference_glsl(vt_ctx):
+    """vt_set_voxelize_thickness(FAT): the CUDA scatter against voxelize.gs compiled with `#define THICKNESS FAT` (:15-19), bit for
+    bit, at 64^3, on a non-cubic grid and at the metric's 512^3; THIN is restored afterwards."""
+    verts, idx = oscene.load_obj(util.BUNNY)
+    bmin, bmax = oscene.mesh_bounds(verts)
+    vt_ctx.set_voxelize_thickness(True)
+    try:
+        for res in [(64, 64, 64), (96, 80, 48), (512, 512, 512)]:
+            M = oscene.mesh_transform(bmin, bmax, res)
+            vt_ctx.voxelize(verts, idx, M, res, fill_offset=0)
+            got = np.packbits(vt_ctx.read_volume() >= 0)
+            assert np.array_equal(got, np.packbits(ref.voxelize(verts, idx, M, res, fat=True) > 0)), res
+            assert np.array_equal(got, np.packbits(vto.voxelize(verts, idx, M, res, fat=True) > 0)), res
+    finally:
+        vt_ctx.set_voxelize_thickness(False)
+    M = oscene.mesh_transform(bmin, bmax, (64, 64, 64))
+    vt_ctx.voxelize(verts, idx, M, (64, 64, 64), fill_offset=0)
+    assert np.array_equal(vt_ctx.read_volume() >= 0, ref.voxelize(verts, idx, M, (64, 64, 64)) > 0)
+    vt_ctx.volume_upload(np.full(16 ** 3, -1, np.int32), (16, 16, 16))

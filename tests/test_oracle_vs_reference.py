@@ -3,6 +3,8 @@
 built-in arithmetic (oracle/vto_math.h), so every result must agree BIT FOR BIT. A mismatch means the restatement
 departed from the shader text (control flow, operand order, RNG consumption, tie handling ...).
 CPU only; the library is prebuilt where /root/reference is absent."""
+import os
+
 import numpy as np
 import pytest
 
@@ -120,3 +122,57 @@ def test_render_pixels_equals_full_frame_both_sides():
     _same(a, full[xy[:, 1], xy[:, 0]])
     assert np.array_equal(h, hits[xy[:, 1], xy[:, 0]])
     _same(ref.render_pixels(s, 3, xy), a)
+
+
+@pytest.mark.skipif(not ref.obj_available(), reason="oracle/_ref/libvt_ref_obj.so not built (needs /root/reference at build time)")
+def test_obj_readers_match_the_reference_tinyobjloader(tmp_path):
+    """The reference's own OBJ reader (thirdParty/tinyobjloader/tiny_obj_loader.cc, compiled unmodified by oracle/shim/Makefile,
+    + the shape merge of mesh/meshLoader.cpp:27-64) pins BOTH restatements: the oracle's (oracle/scene.py load_obj) and the
+    product's MeshLoader::loadFromOBJ (voxeltoy_b200/host/loaders.cpp). bunny.obj, and a file with quads and polygons (fans),
+    negative indices, v/vt/vn and v//vn corners, several groups and objects, comments, exponents and odd white space."""
+    import gzip
+    import voxeltoy_b200 as vt
+    bunny = str(tmp_path / "bunny.obj")
+    with open(bunny, "wb") as f:
+        f.write(gzip.open(util.BUNNY).read())
+    tricky = str(tmp_path / "tricky.obj")
+    with open(tricky, "w") as f:
+        f.write("# comment\nmtllib none.mtl\no first\n"
+                "v 0 0 0\nv 1.5 0 0\nv 1.5e0 1 0\nv 0 1 -2.25E-1\n v   .5\t.5  1 \nv -1 -1 -1\n"
+                "vt 0 0\nvt 1 0\nvt 1 1\nvn 0 0 1\nvn 0 1 0\n"
+                "g quad\nf 1 2 3 4\n"
+                "g mixed\nusemtl m\nf 1/1/1 2/2/1 5/3/2\nf 2//1 3//1 5//2\n"
+                "o second\nv 2 2 2\nv 3 2 2\nv 3 3 2\nv 2 3 2\nv 2.5 3.5 2\n"
+                "f -5 -4 -3 -2 -1\ns off\nf 7 8 9\nf 1 7 10\n"
+                "g dropped\nf 1 2 3\nusemtl other\nf 3 4 5\nf 1 2 3\n")        # usemtl drops the face gathered before it
+    for path in (bunny, tricky):
+        rv, ri = ref.load_obj(path)
+        ov, oi = oscene.load_obj(path)
+        hv, hi = vt.host.load_obj(path)
+        assert ri.size > 0 and ri.size % 3 == 0
+        for name, v, i in (("oracle", ov, oi), ("product", hv, hi)):
+            v = np.asarray(v, np.float32).reshape(-1, 3)
+            assert np.array_equal(np.asarray(i, np.uint32), ri), name + ": indices differ from tinyobjloader on " + os.path.basename(path)
+            assert v.shape == rv.shape and np.array_equal(v.view(np.uint32), rv.view(np.uint32)), name + ": vertices differ on " + os.path.basename(path)
+
+
+def test_fat_voxelizer_matches_reference_glsl():
+    """The FAT variant of voxelize.gs (`#define THICKNESS FAT`, :15-19, :151-163, :170-171, :198-200 -- compiled out in the reference,
+    built here by rewriting that one #define): oracle == shader text on the bunny and on random / degenerate triangles, and every
+    THIN voxel is also a FAT voxel."""
+    verts, idx = oscene.load_obj(util.BUNNY)
+    bmin, bmax = oscene.mesh_bounds(verts)
+    for res in [(32, 32, 32), (64, 64, 64), (96, 80, 48)]:
+        M = oscene.mesh_transform(bmin, bmax, res)
+        a, b = ref.voxelize(verts, idx, M, res, fat=True), vto.voxelize(verts, idx, M, res, fat=True)
+        assert np.array_equal(a > 0, b > 0)
+        thin = vto.voxelize(verts, idx, M, res)
+        assert ((thin > 0) <= (b > 0)).all() and (b > 0).sum() > (thin > 0).sum()
+    rng = np.random.RandomState(2)
+    v = rng.uniform(0.05, 0.95, size=(300, 3)).astype(np.float32)
+    v[::7] = np.round(v[::7] * 16) / 16                                  # vertices on voxel boundaries: the == comparisons of :203-204
+    i = rng.randint(0, 300, size=(400, 3)).astype(np.uint32)
+    i[5] = (1, 1, 2); i[6] = (3, 3, 3)                                   # degenerate
+    M = np.eye(4, dtype=np.float32)
+    for res in [(16, 16, 16), (40, 24, 56)]:
+        assert np.array_equal(ref.voxelize(v, i.reshape(-1), M, res, fat=True) > 0, vto.voxelize(v, i.reshape(-1), M, res, fat=True) > 0)

@@ -84,6 +84,7 @@ SIGNATURES = {
     "vt_reset_counters": (C.c_int, [P]),
     "vt_voxelize": (C.c_int, [P, f32p, C.c_size_t, u32p, C.c_size_t, f32p, C.c_int, C.c_int, C.c_int, C.c_int32]),
     "vt_volume_assign_materials": (C.c_int, [P, i32p, C.c_int, C.c_int]),
+    "vt_set_voxelize_thickness": (C.c_int, [P, C.c_int]),
     "vt_get_last_voxelize_ms": (C.c_int, [P, f32p]),
     "vt_get_last_voxelize_full_ms": (C.c_int, [P, f32p]),
     "vt_pick": (C.c_int, [P, C.c_float, C.c_float]),
@@ -402,6 +403,10 @@ class Context:
         ms = C.c_float()
         self._ck(self.lib.vt_get_last_voxelize_ms(self.h, C.cast(C.byref(ms), f32p)))
         return float(ms.value)
+
+    def set_voxelize_thickness(self, fat):
+        """voxelize.gs:15-19 THICKNESS: False = THIN (the reference's build), True = FAT (conservative)."""
+        self._ck(self.lib.vt_set_voxelize_thickness(self.h, 1 if fat else 0))
 
     def last_voxelize_full_ms(self):
         """Device time of the last vt_voxelize including the id grid and the distance field (scatter only: last_voxelize_ms)."""

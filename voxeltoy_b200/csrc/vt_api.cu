@@ -1022,7 +1022,8 @@ int vt_voxelize(vt_ctx* c, const float* xyz, size_t n_verts, const uint32_t* ind
     if (rc != VT_OK) return rc;
     if (n_tris > 0) {
         const int ctas = std::max(1, std::min((n_tris + 3) / 4, 148 * 16));
-        vt_voxelize_kernel<<<ctas, 128, 0, c->stream>>>(c->d_mesh_xyz, c->d_mesh_idx, n_tris, c->d_mesh_M, X, Y, Z, c->PBX, c->PBX * c->PBY, c->d_bricks);
+        if (c->voxelize_fat) vt_voxelize_kernel<true><<<ctas, 128, 0, c->stream>>>(c->d_mesh_xyz, c->d_mesh_idx, n_tris, c->d_mesh_M, X, Y, Z, c->PBX, c->PBX * c->PBY, c->d_bricks);
+        else vt_voxelize_kernel<false><<<ctas, 128, 0, c->stream>>>(c->d_mesh_xyz, c->d_mesh_idx, n_tris, c->d_mesh_M, X, Y, Z, c->PBX, c->PBX * c->PBY, c->d_bricks);
         c->launches += 1;
     }
     VT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
@@ -1040,6 +1041,13 @@ int vt_voxelize(vt_ctx* c, const float* xyz, size_t n_verts, const uint32_t* ind
     return VT_OK;
 }
 
+int vt_set_voxelize_thickness(vt_ctx* c, int thickness)
+{
+    if (!c) return VT_ERR_INVALID;
+    VT_REQ(c, thickness == VT_VOXELIZE_THIN || thickness == VT_VOXELIZE_FAT, "thickness must be VT_VOXELIZE_THIN or VT_VOXELIZE_FAT");
+    c->voxelize_fat = thickness == VT_VOXELIZE_FAT;
+    return VT_OK;
+}
 int vt_get_last_voxelize_ms(vt_ctx* c, float* ms) { if (!c || !ms) return VT_ERR_INVALID; *ms = c->last_voxelize_ms; return VT_OK; }
 int vt_get_last_voxelize_full_ms(vt_ctx* c, float* ms) { if (!c || !ms) return VT_ERR_INVALID; *ms = c->last_voxelize_full_ms; return VT_OK; }
 

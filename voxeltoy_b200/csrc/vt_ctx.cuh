@@ -81,6 +81,7 @@ struct vt_ctx {
     uint64_t paths = 0, launches = 0;
     // voxelizer timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr; float last_voxelize_ms = 0.f, last_voxelize_full_ms = 0.f, last_env_build_ms = 0.f;
+    bool voxelize_fat = false;                             // voxelize.gs:15-19 THICKNESS (the reference compiles THIN)
     float* d_mesh_xyz = nullptr; unsigned int* d_mesh_idx = nullptr; float* d_mesh_M = nullptr; size_t mesh_verts_cap = 0, mesh_idx_cap = 0;
 };
 

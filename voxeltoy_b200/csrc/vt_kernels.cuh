@@ -316,6 +316,14 @@ VT_DEV float edge_d(f2 n, float va, float vb)                      // voxelize.g
     return dot(n, mk2(0.5f - va, 0.5f - vb)) + 0.5f * gmax(gabs(n.x), gabs(n.y));
 }
 
+VT_DEV float edge_d_fat(f2 n, float va, float vb)                  // voxelize.gs:151-163 (FAT)
+{
+    return (-dot(n, mk2(va, vb)) + gmax(0.0f, n.x)) + gmax(0.0f, n.y);
+}
+
+// FAT = the conservative variant of the same shader (voxelize.gs:15-19, `#define THICKNESS FAT`: adjacent voxels share at
+// least a face); the reference ships it compiled out (THICKNESS THIN)
+template <bool FAT>
 VT_GLOBAL void __launch_bounds__(128)
 vt_voxelize_kernel(const float* __restrict__ xyz_in, const unsigned int* __restrict__ idx, int n_tris,
                    const float* __restrict__ M, int X, int Y, int Z, int BX, int BXY,
@@ -357,12 +365,17 @@ vt_voxelize_kernel(const float* __restrict__ xyz_in, const unsigned int* __restr
         const f2 n0xy = edge_n(n.z, e0.x, e0.y), n1xy = edge_n(n.z, e1.x, e1.y), n2xy = edge_n(n.z, e2.x, e2.y);
         const f2 n0yz = edge_n(n.x, e0.y, e0.z), n1yz = edge_n(n.x, e1.y, e1.z), n2yz = edge_n(n.x, e2.y, e2.z);
         const f2 n0zx = edge_n(n.y, e0.z, e0.x), n1zx = edge_n(n.y, e1.z, e1.x), n2zx = edge_n(n.y, e2.z, e2.x);
-        const float d0xy = edge_d(n0xy, v0.x, v0.y), d1xy = edge_d(n1xy, v1.x, v1.y), d2xy = edge_d(n2xy, v2.x, v2.y);
-        const float d0yz = edge_d(n0yz, v0.y, v0.z), d1yz = edge_d(n1yz, v1.y, v1.z), d2yz = edge_d(n2yz, v2.y, v2.z);
-        const float d0zx = edge_d(n0zx, v0.z, v0.x), d1zx = edge_d(n1zx, v1.z, v1.x), d2zx = edge_d(n2zx, v2.z, v2.x);
+        const float d0xy = FAT ? edge_d_fat(n0xy, v0.x, v0.y) : edge_d(n0xy, v0.x, v0.y), d1xy = FAT ? edge_d_fat(n1xy, v1.x, v1.y) : edge_d(n1xy, v1.x, v1.y),
+                    d2xy = FAT ? edge_d_fat(n2xy, v2.x, v2.y) : edge_d(n2xy, v2.x, v2.y);
+        const float d0yz = FAT ? edge_d_fat(n0yz, v0.y, v0.z) : edge_d(n0yz, v0.y, v0.z), d1yz = FAT ? edge_d_fat(n1yz, v1.y, v1.z) : edge_d(n1yz, v1.y, v1.z),
+                    d2yz = FAT ? edge_d_fat(n2yz, v2.y, v2.z) : edge_d(n2yz, v2.y, v2.z);
+        const float d0zx = FAT ? edge_d_fat(n0zx, v0.z, v0.x) : edge_d(n0zx, v0.z, v0.x), d1zx = FAT ? edge_d_fat(n1zx, v1.z, v1.x) : edge_d(n1zx, v1.z, v1.x),
+                    d2zx = FAT ? edge_d_fat(n2zx, v2.z, v2.x) : edge_d(n2zx, v2.z, v2.x);
         const f3 nP = (n.z < 0.0f) ? -n : n;
         const float dTri = dot(nP, v0);
         const float dThin = dTri - dot(mk2(nP.x, nP.y), mk2(0.5f, 0.5f));
+        const float dFatMin = (dTri - gmax(nP.x, 0.0f)) - gmax(nP.y, 0.0f);       // voxelize.gs:170-171
+        const float dFatMax = (dTri - gmin(nP.x, 0.0f)) - gmin(nP.y, 0.0f);
         const float nzInv = 1.0f / nP.z;
 
         const int wx = hix - lox, wy = hiy - loy;
@@ -373,10 +386,11 @@ vt_voxelize_kernel(const float* __restrict__ xyz_in, const unsigned int* __restr
             const float a0 = d0xy + dot(n0xy, pxy), a1 = d1xy + dot(n1xy, pxy), a2 = d2xy + dot(n2xy, pxy);
             if (!((a0 >= 0.0f) && (a1 >= 0.0f) && (a2 >= 0.0f))) continue;
             const float dot_n_p = dot(mk2(nP.x, nP.y), pxy);
-            const float zInt = (-dot_n_p + dThin) * nzInv;
-            const float zf = floorf(zInt), zc = ceilf(zInt);
-            int zMin = f2i(zf) - ((zf == zInt) ? 1 : 0);
-            int zMax = f2i(zc) + ((zc == zInt) ? 1 : 0);
+            const float zMinInt = FAT ? (-dot_n_p + dFatMin) * nzInv : (-dot_n_p + dThin) * nzInv;     // :195-201
+            const float zMaxInt = FAT ? (-dot_n_p + dFatMax) * nzInv : zMinInt;
+            const float zf = floorf(zMinInt), zc = ceilf(zMaxInt);
+            int zMin = f2i(zf) - ((zf == zMinInt) ? 1 : 0);
+            int zMax = f2i(zc) + ((zc == zMaxInt) ? 1 : 0);
             zMin = max(loz, zMin); zMax = min(hiz, zMax);
             for (int pz = zMin; pz < zMax; ++pz) {
                 const f2 pyz = mk2((float)py, (float)pz), pzx = mk2((float)pz, (float)px);

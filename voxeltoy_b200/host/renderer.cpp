@@ -29,6 +29,7 @@ GPUVoxelizer::~GPUVoxelizer() {}
 bool GPUVoxelizer::voxelizeMesh(const Mesh* mesh, const M44f& meshTransform, const V3i& resolution, vt_ctx* target, int32_t fillOffset)
 {
     if (!m_initialized || !mesh || !target) return false;
+    vt_set_voxelize_thickness(target, (int)m_thickness);
     const int rc = vt_voxelize(target, mesh->vertices().empty() ? NULL : &mesh->vertices()[0], mesh->vertices().size() / 3,
                                mesh->indices().empty() ? NULL : &mesh->indices()[0], mesh->indices().size(),
                                &meshTransform.x[0][0], resolution.x, resolution.y, resolution.z, fillOffset);

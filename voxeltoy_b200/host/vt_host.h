@@ -295,10 +295,14 @@ public:
     // replaces the reference's `GLuint textureUnit` (the bound R32I texture) by the context that owns the grid
     bool voxelizeMesh(const Mesh* mesh, const vtm::M44f& meshTransform, const vtm::V3i& resolution, vt_ctx* target, int32_t fillOffset = 0);
     float lastMilliseconds() const { return m_lastMs; }
+    // voxelize.gs:15-19: the reference selects THIN / FAT by editing `#define THICKNESS`; here it is a property of the voxelizer
+    enum Thickness { THIN = VT_VOXELIZE_THIN, FAT = VT_VOXELIZE_FAT };
+    void setThickness(Thickness t) { m_thickness = t; }
 private:
     bool m_initialized;
     Logger* m_logger;
     float m_lastMs;
+    Thickness m_thickness = THIN;
 };
 vtm::M44f computeMeshTransform(const vtm::Box3f& bounds, const vtm::V3i& voxelResolution);   // renderer/import.cpp:46-64
 
