@@ -509,7 +509,8 @@ def main():
                 x = run_config(args, n2, s2, p2, k2, 3, rank, world, local_rank, dist, full=False)
                 extras[key] = {"value": x["value"], "unit": "Msamples/s", "ms_per_step": x["ms_per_step"], "steps": k2, "scaling": "strong",
                                "config": config_dict(n2, p2, s2, world), "collective_ms": x.get("collective_ms"),
-                               "multi_gpu_check": x["multi_gpu_check"], "kernel_ms_per_step": x["kernel_ms_per_step"]}
+                               "multi_gpu_check": x["multi_gpu_check"], "kernel_ms_per_step": x["kernel_ms_per_step"],
+                               "ms_render_per_step": x["ms_render_per_step"], "ms_combine_per_step_incl_wait": x["ms_combine_per_step_incl_wait"]}
             except Exception as e:                                   # never lose the main line
                 extras[key] = {"value": None, "error": repr(e)}
 

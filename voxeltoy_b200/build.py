@@ -41,7 +41,7 @@ def _sources(d, exts):
 def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     lib = os.path.join(HERE, "libvoxeltoy_b200.so")
-    deps = _sources(CSRC, (".cu", ".cuh", ".h")) + _sources(HOST, (".cpp", ".h")) + [os.path.join(ROOT, "include", "voxeltoy_b200.h")]
+    deps = _sources(CSRC, (".cu", ".cuh", ".h", ".inl")) + _sources(HOST, (".cpp", ".h")) + [os.path.join(ROOT, "include", "voxeltoy_b200.h")]
     if force or _newer(lib, deps):
         cus = _sources(CSRC, (".cu",))
         cpps = _sources(HOST, (".cpp",))

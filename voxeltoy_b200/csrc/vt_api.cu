@@ -813,17 +813,24 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
     // split the passes of this call into batches: at most wf_max_paths paths in flight over all lanes, and at least
     // `lanes` batches when there are enough passes, so that two batches always overlap
     const int lanes = std::max(1, std::min(c->wf_lanes, L.n_passes));
-    // the pools never take more than half of the memory that is free right now (another context, torch or NCCL may share the GPU)
-    size_t budget_paths = c->wf_max_paths;
+    int batch_max;
     {
-        size_t free_b = 0, total_b = 0, held = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            for (int k = 0; k < vt_ctx::kWfLanes; ++k) held += c->wf_capacity[k] * kWfBytesPerPath;
-            budget_paths = std::min(budget_paths, std::max<size_t>((free_b + held) / 2 / kWfBytesPerPath, (size_t)n_items * lanes));
+        const int budget = (int)std::max<size_t>(1, c->wf_max_paths / (size_t)n_items / (size_t)lanes);
+        batch_max = std::max(1, std::min(budget, (L.n_passes + lanes - 1) / lanes));
+        bool grow = false;
+        for (int k = 0; k < lanes; ++k) grow = grow || (size_t)n_items * (size_t)batch_max > c->wf_capacity[k];
+        if (grow) {
+            // the pools never take more than half of the memory that is free right now (another context, torch or NCCL may share
+            // the GPU). Asked only when a pool has to grow: cudaMemGetInfo is a slow driver call when several processes share a box.
+            size_t free_b = 0, total_b = 0, held = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                for (int k = 0; k < vt_ctx::kWfLanes; ++k) held += c->wf_capacity[k] * kWfBytesPerPath;
+                const size_t cap_paths = std::max<size_t>((free_b + held) / 2 / kWfBytesPerPath, (size_t)n_items * lanes);
+                const int budget2 = (int)std::max<size_t>(1, std::min(c->wf_max_paths, cap_paths) / (size_t)n_items / (size_t)lanes);
+                batch_max = std::max(1, std::min(budget2, (L.n_passes + lanes - 1) / lanes));
+            }
         }
     }
-    const int budget = (int)std::max<size_t>(1, budget_paths / (size_t)n_items / (size_t)lanes);
-    int batch_max = std::max(1, std::min(budget, (L.n_passes + lanes - 1) / lanes));
     const int n_iters = F.max_bounces + 3;
     for (;;) {                                        // a smaller batch gives the same bits: halve it when the allocation fails
         int rc = VT_OK;
@@ -846,17 +853,21 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
         VT_CUDA(c, cudaMemsetAsync(cn, 0, sizeof(WfCounts) * (size_t)n_iters, st));
         { WfTimer t(c, VT_K_GENERATE, st);
           const int gen_x = n_items / 256, gen_rows = std::min(nb, std::max(1, (c->wf_sms * 8 + gen_x - 1) / gen_x));   // enough CTAs for every SM, else 1 row
-          wf_generate_kernel<COUNT><<<dim3((unsigned)gen_x, (unsigned)gen_rows), 256, 0, st>>>(V, F, L, S, pass0, nb, cn, prim, c->d_counters); }
+          const dim3 gg((unsigned)gen_x, (unsigned)gen_rows);
+          if (V.skip != nullptr && !COUNT) wf_generate_kernel<COUNT, true><<<gg, 256, 0, st>>>(V, F, L, S, pass0, nb, cn, prim, c->d_counters);
+          else wf_generate_kernel<COUNT, false><<<gg, 256, 0, st>>>(V, F, L, S, pass0, nb, cn, prim, c->d_counters); }
         c->launches += 1;
         for (int it = 0; ; ++it) {
-            // it == 0: primary rays; it >= 1: the shadow + bounce rays emitted by wf_shade(it - 1). Generation `it` of the paths
-            // lives in state[it & 1]; wf_shade compacts its survivors into state[(it + 1) & 1]. Counts block `it` holds the size
-            // of generation `it`, block it + 1 the shade queues wf_trace fills.
-            if (it > 0) { WfTimer t(c, VT_K_OTHER, st); VT_CUDA(c, cudaMemsetAsync(S.vis, 0, vis_bytes, st)); }
-            { WfTimer t(c, VT_K_TRACE, st);
-              if (V.skip != nullptr && !COUNT) wf_trace_kernel<COUNT, true><<<c->wf_trace_blocks[ci], kWfTraceThreads, 0, st>>>(V, F, S, it == 0 ? 1 : 0, cn + it, cn + it + 1, c->d_counters);
-              else wf_trace_kernel<COUNT, false><<<c->wf_trace_blocks[ci], kWfTraceThreads, 0, st>>>(V, F, S, it == 0 ? 1 : 0, cn + it, cn + it + 1, c->d_counters); }
-            c->launches += 1;
+            // it == 0: the primary rays were traced (and routed) by wf_generate; it >= 1: the shadow + bounce rays emitted by
+            // wf_shade(it - 1). Generation `it` of the paths lives in state[it & 1]; wf_shade compacts its survivors into
+            // state[(it + 1) & 1]. Counts block `it` holds the size of generation `it`, block it + 1 the shade queues.
+            if (it > 0) {
+                { WfTimer t(c, VT_K_OTHER, st); VT_CUDA(c, cudaMemsetAsync(S.vis, 0, vis_bytes, st)); }
+                { WfTimer t(c, VT_K_TRACE, st);
+                  if (V.skip != nullptr && !COUNT) wf_trace_kernel<COUNT, true><<<c->wf_trace_blocks[ci], kWfTraceThreads, 0, st>>>(V, F, S, cn + it, cn + it + 1, c->d_counters);
+                  else wf_trace_kernel<COUNT, false><<<c->wf_trace_blocks[ci], kWfTraceThreads, 0, st>>>(V, F, S, cn + it, cn + it + 1, c->d_counters); }
+                c->launches += 1;
+            }
             if (it == 0 && prim != nullptr && pass0 + nb == L.n_passes) {
                 WfTimer t(c, VT_K_OTHER, st);
                 wf_primary_kernel<<<dim3((unsigned)(c->wf_sms * 4), kWfQueues), 256, 0, st>>>(V, F, L, S, pass0, cn + 1, prim);

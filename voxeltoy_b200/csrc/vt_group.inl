@@ -507,7 +507,6 @@ int vt_group_end_combine(vt_group* g, float* rgba_out)
     for (size_t i = 0; i < g->ctx.size(); ++i) { VTG_CUDA(g, cudaSetDevice(g->ctx[i]->device)); VTG_CUDA(g, cudaStreamSynchronize(g->side[i])); }
     if (rl >= 0) {
         VTG_CUDA(g, cudaSetDevice(g->ctx[rl]->device));
-        VTG_CUDA(g, cudaEventElapsedTime(&g->last_exchange_ms, g->t0, g->t1));
         if (rgba_out) VTG_CUDA(g, cudaMemcpy(rgba_out, g->result, g->frame_px * sizeof(float4), cudaMemcpyDeviceToHost));
     }
     g->pending = false;
@@ -519,7 +518,19 @@ int vt_group_read_average(vt_group* g, float* rgba_out)
     return rc != VT_OK ? rc : vt_group_end_combine(g, rgba_out);
 }
 void* vt_group_result_device_ptr(vt_group* g) { return g ? (void*)g->result : nullptr; }
-int vt_group_last_exchange_ms(vt_group* g, float* ms) { if (!g || !ms) return VT_ERR_INVALID; *ms = g->last_exchange_ms; return VT_OK; }
+// device time of the most recent exchange on the root's side stream (waits for it); 0 in processes that do not hold rank 0
+int vt_group_last_exchange_ms(vt_group* g, float* ms)
+{
+    if (!g || !ms) return VT_ERR_INVALID;
+    const int rl = group_root_local(g);
+    if (rl >= 0 && g->t0 && g->frame_px != 0) {
+        VTG_CUDA(g, cudaSetDevice(g->ctx[rl]->device));
+        VTG_CUDA(g, cudaEventSynchronize(g->t1));
+        VTG_CUDA(g, cudaEventElapsedTime(&g->last_exchange_ms, g->t0, g->t1));
+    }
+    *ms = g->last_exchange_ms;
+    return VT_OK;
+}
 // bytes the root receives from the other ranks per combination (what crosses NVLink)
 size_t vt_group_exchange_bytes(const vt_group* g)
 {

@@ -216,6 +216,41 @@ VT_DEV unsigned int wf_reserve_slot(WfCounts* __restrict__ cnt, bool want, WfBlo
     return sm.base + wt + (unsigned)__popc(mt & lt);
 }
 
+// wf_generate: one slot of generation 0 and one position in the shade queue `q` per thread with `want`, aggregated the same way
+// (counter 0 = slots, counters 1..5 = the queues; lanes 0..5 of a warp each carry one counter through the shared-memory stage).
+struct WfBlockCounters6 { unsigned int cnt[1 + kWfQueues], base[1 + kWfQueues]; };
+VT_DEV void wf_reserve6_init(WfBlockCounters6& sm)
+{
+    if (threadIdx.x < 1 + kWfQueues) sm.cnt[threadIdx.x] = 0u;
+    __syncthreads();
+}
+VT_DEV void wf_reserve_slot_and_queue(WfCounts* __restrict__ cnt, WfCounts* __restrict__ cq, bool want, int q, WfBlockCounters6& sm,
+                                      unsigned int& slot, unsigned int& qpos)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned mv = __ballot_sync(full, want);
+    unsigned mine = 0u, carried = (lane == 0) ? mv : 0u;               // mask of the lanes that share my queue / of the counter this lane carries
+    #pragma unroll
+    for (int k = 0; k < kWfQueues; ++k) {
+        const unsigned m = __ballot_sync(full, want && q == k);
+        if (want && q == k) mine = m;
+        if (lane == 1 + k) carried = m;
+    }
+    unsigned int wb = 0;
+    if (lane < 1 + kWfQueues && carried != 0u) wb = atomicAdd(&sm.cnt[lane], (unsigned)__popc(carried));
+    const unsigned int wb_slot = __shfl_sync(full, wb, 0), wb_q = __shfl_sync(full, wb, want ? 1 + q : 0);
+    __syncthreads();
+    if (threadIdx.x < 1 + kWfQueues && sm.cnt[threadIdx.x] != 0u) {
+        sm.base[threadIdx.x] = atomicAdd(threadIdx.x == 0 ? &cnt->tq : &cq->sq[threadIdx.x - 1], sm.cnt[threadIdx.x]);
+        sm.cnt[threadIdx.x] = 0u;                                       // ready for the next call (visible after the barrier below)
+    }
+    __syncthreads();
+    slot = sm.base[0] + wb_slot + (unsigned)__popc(mv & lt);
+    qpos = want ? sm.base[1 + q] + wb_q + (unsigned)__popc(mine & lt) : 0u;
+}
+
 template <bool COUNT>
 VT_DEV void wf_flush_tally(const Tally<COUNT>& tl, Counters* __restrict__ counters)
 {
@@ -238,17 +273,25 @@ VT_DEV void wf_flush_tally(const Tally<COUNT>& tl, Counters* __restrict__ counte
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// wf_generate: pathTracer.fs:172-196 + dda.h:16-34 of the primary ray. grid = (n_items / 256, rows): a thread generates every rows-th pass of its pixel;
-// rows = 1 whenever the frame alone fills the machine (1 / 2 / 4 / 8 / 16 rows measured at 1080p: 12.4 / 12.5 / 12.7 / 13.3 / 14.3 ms).
-// Pixels whose ray misses the volume's box are finished here; every other pixel gets a slot of generation 0.
+// wf_generate: pathTracer.fs:172-208 -- RNG offset, camera ray, slab test, and the WHOLE traversal of the primary ray (dda.h:16-57).
+// Primary rays of neighbouring pixels are coherent (the threads of a warp cover an 8x4 pixel block of one pass), so their DDA
+// runs here in lockstep at nearly full width; this spares a 40-byte ray record, its trip through wf_trace's refill / retire
+// machinery and the queue hand-over for a third of all rays (round 2: generate + first trace 10.2 -> see DESIGN.md per 64-pass
+// batch). The finished primary path is routed to its shade queue right away (:202-208, :214).
+// grid = (n_items / 256, rows): a thread generates every rows-th pass of its pixel; rows = 1 whenever the frame alone fills
+// the machine. Pixels whose ray misses the volume's box are finished here; every other pixel gets a slot of generation 0.
 // ---------------------------------------------------------------------------------------------------------
-template <bool COUNT>
-VT_GLOBAL void __launch_bounds__(256)
+#ifndef VT_WF_GENERATE_MIN_BLOCKS
+#define VT_WF_GENERATE_MIN_BLOCKS 3
+#endif
+template <bool COUNT, bool SKIP>
+VT_GLOBAL void __launch_bounds__(256, VT_WF_GENERATE_MIN_BLOCKS)
 wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, int pass0, int n_batch,
                    WfCounts* __restrict__ cnt, int* __restrict__ primary, Counters* __restrict__ counters)
 {
-    __shared__ WfBlockCounter sm;
-    wf_reserve_init(sm);
+    __shared__ WfBlockCounters6 sm;
+    wf_reserve6_init(sm);
+    const unsigned full = 0xffffffffu;
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     Tally<COUNT> tl; tl.clear();
     int px = 0, py = 0;
@@ -266,7 +309,8 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
         f3 ro = mk3(0.f), rd = mk3(0.f);
         int2 rng = make_int2(0, 0);
         Dda s;
-        s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.sx = s.sy = s.sz = 1; s.dx = s.dy = s.dz = s.ex = s.ey = s.ez = 0.f;
+        s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.steps = 0; s.bkey = -1; s.brick = 0ull;
+        s.sx = s.sy = s.sz = 1; s.dx = s.dy = s.dz = s.ex = s.ey = s.ez = 0.f;
         if (mine) {
             valid = true;
             const int sample = L.first_sample + (pass0 + pass_local) * L.sample_stride;
@@ -287,12 +331,44 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
             }
             if (primary != nullptr && pass0 + pass_local == L.n_passes - 1) primary[(size_t)px + (size_t)py * (size_t)F.W] = -1;
         }
-        const unsigned int slot = wf_reserve_slot(cnt, valid, sm);
+        // ---- the primary traversal, in lockstep (dda.h:38-57) ----------------------------------------------------
+        {
+            int guard = (V.X + V.Y + V.Z) / 16 + 8;                                    // belt and braces: see dda_begin on why rays always leave
+            for (;;) {
+                const bool running = valid && status == DDA_RUNNING;
+                if (__ballot_sync(full, running) == 0u) break;
+                if (running) {
+                    #pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        status = dda_step<COUNT>(V, s, tl);
+                        if (status != DDA_RUNNING) break;
+                    }
+                    if (--guard < 0 && status == DDA_RUNNING) status = DDA_NOHIT;
+                }
+                if (SKIP && !COUNT) {                                                  // exact empty-space skip, as in wf_trace
+                    const bool run2 = valid && status == DDA_RUNNING;
+                    const int radius = run2 ? dda_skip_radius(V, s) : 0;
+                    const unsigned m_running = __ballot_sync(full, run2), m_want = __ballot_sync(full, dda_skip_wanted(radius));
+                    if (m_want != 0u && (__popc(m_want) >= kWfSkipMinLanes || 2 * __popc(m_want) >= __popc(m_running))) {
+                        if (dda_skip_wanted(radius)) (void)dda_skip(V, s, radius);
+                    }
+                }
+            }
+        }
+        // ---- routing (:202-208, :214): one slot of generation 0 and one shade-queue entry per path ---------------------
+        int q = 0, flags = 0;
+        if (valid) {
+            flags = wf_hit_flags(status, s) | WF_HIT_PRIMARY;
+            q = wf_route(V, F, flags, -1, s.ix, s.iy, s.iz);
+        }
+        unsigned int slot, qpos;
+        wf_reserve_slot_and_queue(cnt, cnt + 1, valid, q, sm, slot, qpos);
         if (valid) {
             // a primary path has radiance 0, throughput 1, nothing pending, bounce 0, no BSDF pdf: wf_shade synthesises all of that
             // from the PRIMARY flag, and only the first sector of the record is written
             st_stream32(S.state[0] + 4 * (size_t)slot, make_float4(ro.x, ro.y, ro.z, rd.x), make_float4(rd.y, rd.z, 0.0f, 0.0f));
-            wf_store_ray(S, 1, slot, status, s, WF_RAY_PRIMARY, 0, (int)pid, wf_rng_pack(F, rng));
+            st_stream16(S.sq[q] + qpos, wf_entry(slot, s, flags, pid));
+            st_stream4(S.sq_rng[q] + qpos, wf_rng_pack(F, rng));
         }
     }
     wf_flush_tally<COUNT>(tl, counters);
@@ -312,7 +388,7 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
 #endif
 template <bool COUNT, bool SKIP>
 VT_GLOBAL void __launch_bounds__(kWfTraceThreads, VT_WF_TRACE_MIN_BLOCKS)
-wf_trace_kernel(const Volume V, const Frame F, const WfState S, const int primary_only,
+wf_trace_kernel(const Volume V, const Frame F, const WfState S,
                 WfCounts* __restrict__ cnt, WfCounts* __restrict__ cnext, Counters* __restrict__ counters)
 {
     // per-warp cursors into the shade queues: [next, end) of the chunk the warp is filling (warp-uniform, touched by lane 0)
@@ -327,7 +403,7 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S, const int primar
     if (lane < kWfQueues) { cur_next[warp][lane] = 0u; cur_end[warp][lane] = 0u; }
     __syncwarp();
     const unsigned int n = cnt->tq;                                   // slots of this generation
-    const unsigned int w_first = primary_only ? n : 0u, w_total = 2u * n;
+    const unsigned int w_total = 2u * n;
     unsigned int* __restrict__ vis = S.vis;
     Tally<COUNT> tl; tl.clear();
 
@@ -400,7 +476,7 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S, const int primar
             if (range_next >= range_end) {
                 unsigned base = 0;
                 if (lane == 0) base = atomicAdd(&cnt->work, (unsigned)kWfGrab);
-                base = __shfl_sync(full, base, 0) + w_first;
+                base = __shfl_sync(full, base, 0);
                 range_next = base;
                 range_end = min(base + (unsigned)kWfGrab, w_total);
                 if (base >= w_total) { exhausted = true; range_end = range_next = 0; }
