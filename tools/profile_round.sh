@@ -10,7 +10,7 @@ tail -c 1500 gpurun_out/${tag}_bench.json
 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 120 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --passes 64 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_under_ncu.log 2>&1
 # one batch (5 launches) of the two big kernels, full set
-for k in wf_trace wf_shade; do
+for k in wf_generate wf_trace wf_shade; do
 ncu --set full --clock-control none --import-source on -k regex:$k -s 30 -c 5 -o gpurun_out/${tag}_$k \
     python bench.py --passes 64 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_$k.log 2>&1
 done
