@@ -77,7 +77,9 @@ def c4():
         r.setPartition(vt.VT_PART_TILES, rank, 8); r.resetRender(); r.renderPasses(8); acc += ctx.read_average()
     r.setPartition(vt.VT_PART_NONE, 0, 1)
     same = bool(((acc.view(np.uint32) == full.view(np.uint32)) | (np.isnan(acc) & np.isnan(full))).all())
-    out = dict(config="C4 terrain 256^3, 4K, 8 bounces, tiles", emissive=int(len(em)), msamples_per_s=3840 * 2160 * 8 / dt / 1e6,
+    ctx.kernel_timing_enable(True); ctx.kernel_times(); r.resetRender(); r.renderPasses(8); ctx.sync()
+    kt = {k: round(v[0], 2) for k, v in ctx.kernel_times().items()}; ctx.kernel_timing_enable(False)
+    out = dict(config="C4 terrain 256^3, 4K, 8 bounces, tiles", emissive=int(len(em)), msamples_per_s=3840 * 2160 * 8 / dt / 1e6, kernel_ms=kt,
                tiles_equal_full_bit_exact=same)
     r.close(); return out
 

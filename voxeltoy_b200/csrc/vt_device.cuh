@@ -317,13 +317,48 @@ VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
 // untouched), and the ordinary loop takes over for the last few steps.
 // The box comes from the distance fields of Volume: a cube of (2k-1) cells around the ray's cell, clipped to the volume.
 //
-// advance_until: d <- fl(d + e) while d <= tau, at most nmax times; returns the number of additions. The additions are simply
-// performed, four per trip: 2 instructions per skipped addition against 27 for a full DDA step. The values increase
-// monotonically (e > 0), so four additions may be taken at once iff the third result is still <= tau.
-// (Round 1 replaced long runs by a closed form -- inside one binade a rounded addition of a constant moves the significand by
-// a constant integer -- but its set-up ran on ~8 lanes per instruction and was 54 % of wf_trace's instructions on the 512^3
-// bunny, profiles/r02_c3_v17_*; with the distance field capped at 16 cells a run is at most 127 additions = 32 trips.)
-VT_DEV int advance_until(float& d, float e, float tau, int nmax)
+// advance_binade: d <- fl(d + e) while d <= tau, at most nmax times in total (k counts the additions), for a threshold tau that
+// does not lie beyond the binade of d: every addition that is made then has its operand in that one binade. Round 2 first
+// performed the additions one by one (2 instructions each): on the 512^3 bunny a skip replaces 35 DDA iterations on average,
+// the lanes of a warp need very different numbers of them, and the addition loops ran at 6 of 32 lanes -- 40 % of wf_trace's
+// instructions (profiles/r02_c3_v18_*). Now a run of additions is ONE integer multiply-add on the bit pattern, in straight-line
+// code that every lane of the warp executes together:
+//   d = M u with u the unit in the last place of the binade and M the 24-bit significand; e = (q + f) u, 0 <= f < 1. While
+//   the sum stays in the binade, fl(d + e) = (M + q + [f > 1/2]) u; on a tie (f = 1/2) the sum goes to the EVEN neighbour.
+//   After one addition made inside the binade the significand is even in the tie case, and from an even M a tie adds
+//   q + (q & 1), leaving M even: from then on the bit pattern moves by a constant `inc` per addition, tie or no tie.
+// So: three real additions (operands d, d1, d2 inside the binade, hence d2 settled), inc = bits(d3) - bits(d2), then
+// floor((bits(tau) - bits(d3)) / inc) further additions in one step (each starts at or below tau and ends at or below tau, i.e.
+// inside the binade), then the one real addition that carries d beyond tau -- possibly into the next binade, which is why it is
+// a real one. A degenerate increment (e below half an ulp of d: d would never move) leaves the run unfinished and the caller
+// abandons the skip. Checked against the literal loop on the device (vt_debug_advance, tests/test_gpu_configs.py) on 400 k realistic
+// and adversarial operand sets, and on the CPU by tests/test_skip_closed_form.py (the same integer algebra in numpy).
+VT_DEV void advance_binade(float& d, int& k, const float e, const float tau, const int nmax)
+{
+    if (d <= tau && k < nmax) { d = d + e; k += 1; }
+    if (d <= tau && k < nmax) { d = d + e; k += 1; }
+    const int b2 = __float_as_int(d);
+    const bool third = d <= tau && k < nmax;
+    if (third) { d = d + e; k += 1; }
+    const int b3 = __float_as_int(d);
+    const int inc = b3 - b2;
+    // qd = floor(N / inc), 0 <= N < 2^23: approximate quotient (one MUFU), exact after one correction each way; a quotient too
+    // large for that (>= 2^20) is clamped to nmax - k below whatever its last digits are
+    const int N = __float_as_int(tau) - b3, ic = max(inc, 1);
+    float rcp;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"((float)ic));
+    int qd = __float2int_rz((float)N * rcp);
+    const int rem = N - qd * ic;
+    if (rem < 0) qd -= 1;
+    if (rem >= ic) qd += 1;
+    const int J = min(qd, nmax - k);
+    if (third && d <= tau && inc > 0 && J > 0) { d = __int_as_float(b3 + J * inc); k += J; }
+    if (d <= tau && k < nmax) { d = d + e; k += 1; }
+}
+// The additions themselves, four per trip (the values increase, so four may be taken at once iff the third result is still <= tau):
+// 2 instructions per addition. Right for COHERENT rays -- the primary rays wf_generate traces in lockstep, whose lanes need about
+// the same number of additions -- and free of the closed form's one-binade limit, which costs rays that start at t = 0 several calls.
+VT_DEV int advance_additions(float& d, float e, float tau, int nmax)
 {
     int k = 0;
     while (k + 4 <= nmax) {
@@ -332,6 +367,20 @@ VT_DEV int advance_until(float& d, float e, float tau, int nmax)
         d = a3 + e; k += 4;
     }
     while (d <= tau && k < nmax) { d = d + e; ++k; }
+    return k;
+}
+// last float of the binade of a non-negative t (of the denormal range for t < 2^-126: the bit patterns are linear there too)
+VT_DEV float binade_end(float t) { return __int_as_float(__float_as_int(t) | 0x7fffff); }
+
+// the test hook's single-axis form: binade after binade
+VT_DEV int advance_until(float& d, float e, float tau, int nmax)
+{
+    int k = 0;
+    while (d <= tau && k < nmax) {
+        const int k0 = k;
+        if (__float_as_int(d) >= 0) advance_binade(d, k, e, gmin(tau, binade_end(d)), nmax);
+        if (k == k0) { d = d + e; k += 1; }                       // -0 (its "binade" lies below it): one real addition
+    }
     return k;
 }
 
@@ -344,8 +393,13 @@ VT_DEV int dda_skip_radius(const Volume& V, const Dda& s)
 #ifndef VT_SKIP_MAX_ADD
 #define VT_SKIP_MAX_ADD 128
 #endif
+#ifndef VT_SKIP_PASSES
+#define VT_SKIP_PASSES 1
+#endif
 VT_DEV bool dda_skip_wanted(int v) { return v >= (2 << 2) || (v & 3) >= 2; }
-VT_DEV int dda_skip(const Volume& V, Dda& s, int v)      // v = dda_skip_radius with dda_skip_wanted(v); returns the number of steps skipped
+// v = dda_skip_radius with dda_skip_wanted(v); returns the number of steps skipped
+template <bool COHERENT>
+VT_DEV int dda_skip(const Volume& V, Dda& s, int v)
 {
     // the far field (8^3 cells) when it allows a skip at all, else the near field (4^3 bricks)
     const int k8 = v >> 2;
@@ -362,11 +416,34 @@ VT_DEV int dda_skip(const Volume& V, Dda& s, int v)      // v = dda_skip_radius 
     // first value at which axis a would step OUT of the box: D_a(n_a) ~ d_a + n_a e_a; stay 0.1 % below the smallest
     const float tau = gmin(s.dx + (float)nx * s.ex, gmin(s.dy + (float)ny * s.ey, s.dz + (float)nz * s.ez)) * 0.999f;
     if (!(tau > gmin(s.dx, gmin(s.dy, s.dz))) || !(tau < 3.0e38f)) return 0;
+    // Incoherent rays (wf_trace): one pass = the run up to the end of the binade of the smallest dis (or to tau), straight-line
+    // code for the whole warp. More passes per call (VT_SKIP_PASSES) or calls in a row were slower on the 512^3 bunny and the 256^3
+    // terrain alike (trace 68.9 -> 81.6 ms with two passes): a ray that stopped at a binade boundary continues at its next skip.
+    // A pass that leaves an axis unfinished (the box ended before tau, or a degenerate increment) is dropped.
     float dx = s.dx, dy = s.dy, dz = s.dz;
-    const int kx = advance_until(dx, s.ex, tau, nx);
-    const int ky = advance_until(dy, s.ey, tau, ny);
-    const int kz = advance_until(dz, s.ez, tau, nz);
-    if (dx <= tau || dy <= tau || dz <= tau) return 0;            // an axis ran out of box before tau: abandon, state untouched
+    int kx = 0, ky = 0, kz = 0, done = 0;
+    if (COHERENT) {
+        kx = advance_additions(dx, s.ex, tau, nx);
+        ky = advance_additions(dy, s.ey, tau, ny);
+        kz = advance_additions(dz, s.ez, tau, nz);
+        if (dx <= tau || dy <= tau || dz <= tau) return 0;        // an axis ran out of box before tau: abandon, state untouched
+        done = 1;
+    } else
+    #pragma unroll 1
+    for (int pass = 0; pass < VT_SKIP_PASSES; ++pass) {
+        const float tmin = gmin(dx, gmin(dy, dz));
+        const float tc = gmin(tau, binade_end(tmin));
+        if (!(tc > tmin) || __float_as_int(tmin) < 0) break;
+        float ax = dx, ay = dy, az = dz;
+        int jx = kx, jy = ky, jz = kz;
+        advance_binade(ax, jx, s.ex, tc, nx);
+        advance_binade(ay, jy, s.ey, tc, ny);
+        advance_binade(az, jz, s.ez, tc, nz);
+        if (ax <= tc || ay <= tc || az <= tc) break;
+        dx = ax; dy = ay; dz = az; kx = jx; ky = jy; kz = jz; done = 1;
+        if (tc == tau) break;
+    }
+    if (!done) return 0;
     s.dx = dx; s.dy = dy; s.dz = dz;
     s.ix += s.sx * kx; s.iy += s.sy * ky; s.iz += s.sz * kz;
     return kx + ky + kz;

@@ -350,7 +350,7 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
                     const int radius = run2 ? dda_skip_radius(V, s) : 0;
                     const unsigned m_running = __ballot_sync(full, run2), m_want = __ballot_sync(full, dda_skip_wanted(radius));
                     if (m_want != 0u && (__popc(m_want) >= kWfSkipMinLanes || 2 * __popc(m_want) >= __popc(m_running))) {
-                        if (dda_skip_wanted(radius)) (void)dda_skip(V, s, radius);
+                        if (dda_skip_wanted(radius)) (void)dda_skip<true>(V, s, radius);
                     }
                 }
             }
@@ -408,7 +408,7 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S,
     Tally<COUNT> tl; tl.clear();
 
 #ifdef VT_SKIP_STATS
-    unsigned long long dbg_calls = 0, dbg_ok = 0, dbg_steps = 0;
+    unsigned long long dbg_calls = 0, dbg_ok = 0, dbg_steps = 0, dbg_plain = 0, dbg_long = 0;
 #endif
     bool have = false, exhausted = false;
     unsigned int range_next = 0, range_end = 0;     // warp-uniform
@@ -506,21 +506,24 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S,
                 #pragma unroll
                 for (int k = 0; k < kChunk; ++k) {
                     status = dda_step<COUNT>(V, s, tl);
+#ifdef VT_SKIP_STATS
+                    dbg_plain += 1;
+#endif
                     if (status != DDA_RUNNING) break;
                 }
                 if (--guard < 0 && status == DDA_RUNNING) status = DDA_NOHIT;
             }
             if (SKIP && !COUNT) {                 // counting builds step every voxel so that S stays the algorithmic count
                 // the cheap part (one byte per lane) runs converged; the skip itself only when enough lanes want it, so that its
-                // divergent set-up is not paid for one or two lanes while the rest of the warp idles
+                // set-up is not paid for one or two lanes while the rest of the warp idles
                 const bool running = have && status == DDA_RUNNING;
                 const int radius = running ? dda_skip_radius(V, s) : 0;
                 const unsigned m_running = __ballot_sync(full, running), m_want = __ballot_sync(full, dda_skip_wanted(radius));
                 if (m_want != 0u && (__popc(m_want) >= kWfSkipMinLanes || 2 * __popc(m_want) >= __popc(m_running))) {
                     if (dda_skip_wanted(radius)) {
-                        const int skipped = dda_skip(V, s, radius);
+                        const int skipped = dda_skip<false>(V, s, radius);
 #ifdef VT_SKIP_STATS
-                        dbg_calls += 1; dbg_ok += skipped > 0; dbg_steps += skipped;
+                        dbg_calls += 1; dbg_ok += skipped > 0; dbg_steps += skipped; dbg_long += skipped >= 32;
 #else
                         (void)skipped;
 #endif
@@ -571,7 +574,7 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S,
         for (unsigned i = cur_next[warp][k] + (unsigned)lane; i < cur_end[warp][k]; i += 32u)
             S.sq[k][i] = make_int4((int)kWfInvalid, 0, 0, 0);
 #ifdef VT_SKIP_STATS
-    if (SKIP) { atomicAdd(&counters->E, dbg_calls); atomicAdd(&counters->Q, dbg_ok); atomicAdd(&counters->H, dbg_steps); }
+    if (SKIP) { atomicAdd(&counters->E, dbg_calls); atomicAdd(&counters->Q, dbg_ok); atomicAdd(&counters->H, dbg_steps); atomicAdd(&counters->S, dbg_plain); atomicAdd(&counters->R, dbg_long); }
 #endif
     wf_flush_tally<COUNT>(tl, counters);
 }
