@@ -332,15 +332,23 @@ def run_config(args, name, scaling, passes, steps, warmup, rank, world, local_ra
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = samples_per_step * steps / (ms_total * 1e-3) / 1e6
-
     ms_render = sum(x.elapsed_time(y) for x, y in split["render"]) / steps
     ms_combine = sum(x.elapsed_time(y) for x, y in split["combine"]) / steps
-    out = {"value": value, "ms_per_step": ms_total / steps, "ms_render_per_step": ms_render, "ms_combine_per_step_incl_wait": ms_combine, "wall_s": t_wall, "clocks": clocks, "gpu_launches": int(launches),
+
+    per_rank = None
+    if world > 1:
+        # where a step's time goes on every rank: its own kernels, its render calls (kernels + launch gaps), the exchange + the wait
+        # for the slowest rank, and the step as a whole
+        mine = {"rank": rank, "ms_step": ms_steps / steps, "ms_render": ms_render, "ms_combine_incl_wait": ms_combine, "ms_kernels": kernel_ms_total / steps}
+        box = [None] * world
+        dist.all_gather_object(box, mine)
+        per_rank = box
+    out = {"value": value, "ms_per_step": ms_total / steps, "ms_render_per_step": ms_render, "ms_combine_per_step_incl_wait": ms_combine, "per_rank": per_rank, "wall_s": t_wall, "clocks": clocks, "gpu_launches": int(launches),
            "kernel_ms_per_step": {k: v[0] / steps for k, v in ktimes.items()}, "multi_gpu_check": check,
            "local_passes_per_step": local_passes, "edits_per_step": (edits["n"] / float(steps + warmup)) if edit_every else 0}
     if grp is not None:
         per_step = (local_passes + reduce_every - 1) // reduce_every
-        out["collective_ms"] = {"per_exchange_device": float(np.mean(ex_ms)) if ex_ms else None, "exchanges_per_step": per_step,
+        out["collective_ms"] = {"per_exchange_device": float(np.mean(ex_ms)) if ex_ms else None, "per_exchange_device_each_step": [float(x) for x in ex_ms], "exchanges_per_step": per_step,
                                 "bytes_to_root_per_exchange": grp.exchange_bytes(), "exchange": "nccl" if grp.exchange() == 0 else "peer",
                                 "how": "cudaEvents on the root's side stream around snapshot -> %s -> normalise" %
                                        ("pack tiles + ncclSend/ncclRecv gather + unpack" if mode == vtgroup.PART_TILES else "ncclReduce(sum)"),
@@ -510,7 +518,8 @@ def main():
                 extras[key] = {"value": x["value"], "unit": "Msamples/s", "ms_per_step": x["ms_per_step"], "steps": k2, "scaling": "strong",
                                "config": config_dict(n2, p2, s2, world), "collective_ms": x.get("collective_ms"),
                                "multi_gpu_check": x["multi_gpu_check"], "kernel_ms_per_step": x["kernel_ms_per_step"],
-                               "ms_render_per_step": x["ms_render_per_step"], "ms_combine_per_step_incl_wait": x["ms_combine_per_step_incl_wait"]}
+                               "ms_render_per_step": x["ms_render_per_step"], "ms_combine_per_step_incl_wait": x["ms_combine_per_step_incl_wait"],
+                               "per_rank": x.get("per_rank")}
             except Exception as e:                                   # never lose the main line
                 extras[key] = {"value": None, "error": repr(e)}
 
@@ -532,6 +541,7 @@ def main():
             line["ms_render_per_step"] = res["ms_render_per_step"]
             line["ms_combine_per_step_incl_wait"] = res["ms_combine_per_step_incl_wait"]    # includes waiting for the slowest rank to arrive
             line["multi_gpu_check"] = res["multi_gpu_check"]
+            line["per_rank"] = res.get("per_rank")
             if extras:
                 line["extras"] = extras
         if name == "c5":

@@ -629,9 +629,10 @@ static Volume make_volume(const vt_ctx* c)
 {
     Volume V;
     V.ids8 = c->id_bytes == 1 ? (const uint8_t*)c->d_ids : nullptr; V.ids16 = c->id_bytes == 2 ? (const uint16_t*)c->d_ids : nullptr;
-    V.id_offset = c->d_id_offset; V.bricks = c->d_bricks;
+    V.id_offset = c->d_id_offset; V.bricks = c->d_bricks; V.bricks_top = c->d_bricks_alloc;
     V.X = c->X; V.Y = c->Y; V.Z = c->Z;
     V.BX = c->PBX; V.BXY = c->PBX * c->PBY;               // strides of the padded brick array
+    V.nBX = -V.BX; V.nBXY = -V.BXY;
     const bool skip = c->dist_valid && skip_wanted(c);
     V.skip = skip ? c->d_skip : nullptr; V.SX = c->BX; V.SXY = c->BX * c->BY;
     V.bmin.x = c->bmin[0]; V.bmin.y = c->bmin[1]; V.bmin.z = c->bmin[2];

@@ -27,8 +27,10 @@ struct Volume {
     const uint16_t* __restrict__ ids16;
     const int32_t* __restrict__ id_offset; // id -> offset into the material array
     const unsigned long long* __restrict__ bricks;   // brick (0,0,0) of the padded array
+    const unsigned long long* __restrict__ bricks_top;   // brick (-1,-1,-1) = the first word of the padded array; dda_step indexes downwards from here with its tag
     int X, Y, Z;
     int BX, BXY;                           // strides of the padded brick array
+    int nBX, nBXY;                         // -BX, -BXY (dda_step)
     // empty-space skip field (dda_skip), one byte per 4^3 brick (unpadded, x fastest): bits 2..7 = k8, the Chebyshev distance
     // field over 8^3-voxel cells (0 = the cell holds a solid voxel, k >= 1 = every cell within distance k-1 is empty, capped);
     // bits 0..1 = k4, the same over 4^3 bricks capped at 3 (the near field: thin shells leave rays within two 8^3 cells of a
@@ -201,28 +203,41 @@ __device__ __noinline__ bool raymarch_slow(const Volume& V, f3 vp, f3 dis, f3 sg
 // (mask*sign)*inc of dda.h:52 is +-inc = |1/d| for a stepping axis and +-0 otherwise, so the float
 // state `dis` is advanced by exactly the additions the shader performs.
 struct Dda {
-    int ix, iy, iz;            // voxel position (hit position when done)
+    // voxel position (hit position when done), kept the way the stepping loop wants it: complemented and pre-shifted into the
+    // fields of the in-brick bit index -- cx = ~ix, cy = ~iy << 2, cz = ~iz << 4 -- so that the index of the voxel's bit, counted
+    // from the sign position, is three masked ORs: (cx & 3) | (cy & 0xc) | (cz & 0x30) = 63 - ((ix&3) | (iy&3)<<2 | (iz&3)<<4)
+    int cx, cy, cz;
     float dx, dy, dz;          // dis
     float ex, ey, ez;          // sign*inc per axis
-    int sx, sy, sz;            // integer sign
+    int nsx, nsy, nsz;         // what a step adds to cx, cy, cz: -sign, -4 sign, -16 sign
     int steps;
-    int bkey;                  // cached brick index (-1 none)
+    int bkey;                  // cached brick tag (-1 none)
     unsigned long long brick;  // cached 4x4x4 occupancy word
     int nanmask;               // bit i: component i of the (float) position is NaN (only via the slow path)
+    VT_DEV int ix() const { return ~cx; }
+    VT_DEV int iy() const { return ~(cy >> 2); }
+    VT_DEV int iz() const { return ~(cz >> 4); }
+    VT_DEV void set_pos(int x, int y, int z) { cx = ~x; cy = (~y) << 2; cz = (~z) << 4; }
+    VT_DEV void set_sign(int sx, int sy, int sz) { nsx = -sx; nsy = -4 * sy; nsz = -16 * sz; }
+    VT_DEV bool pos_x() const { return nsx < 0; }     // the ray moves towards +x
+    VT_DEV bool pos_y() const { return nsy < 0; }
+    VT_DEV bool pos_z() const { return nsz < 0; }
+    VT_DEV void advance(int kx, int ky, int kz) { cx += nsx * kx; cy += nsy * ky; cz += nsz * kz; }   // kx steps along x, ...
 };
 enum { DDA_RUNNING = 0, DDA_HIT = 1, DDA_NOHIT = 2 };
+constexpr int kNoBrick = -1;             // Dda::bkey when no brick word is cached (brick indices are >= 0)
 
 VT_DEV f3 dda_position(const Dda& s)
 {
     const float qn = __int_as_float(0x7fc00000);
-    return mk3((s.nanmask & 1) ? qn : (float)s.ix, (s.nanmask & 2) ? qn : (float)s.iy, (s.nanmask & 4) ? qn : (float)s.iz);
+    return mk3((s.nanmask & 1) ? qn : (float)s.ix(), (s.nanmask & 2) ? qn : (float)s.iy(), (s.nanmask & 4) ? qn : (float)s.iz());
 }
 
 // dda.h:16-34. Returns DDA_RUNNING when stepping must follow, else the final status (position in s).
 template <bool COUNT>
 VT_DEV int dda_begin(const Volume& V, f3 o, f3 d, Dda& s, Tally<COUNT>& tl)
 {
-    s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.steps = 0; s.bkey = -1; s.brick = 0ull;   // hit_pos = 0 on the early-out path (contract U1)
+    s.set_pos(0, 0, 0); s.nanmask = 0; s.steps = 0; s.bkey = kNoBrick; s.brick = 0ull;   // hit_pos = 0 on the early-out path (contract U1)
     o = o + gsign(d) * 0.001f;                                    // :19
     const f3 vo = ((o - V.bmin) * V.inv_extent) * V.resf;         // :16,:20
     const f3 vp = gfloor(vo);                                     // :22
@@ -242,11 +257,11 @@ VT_DEV int dda_begin(const Volume& V, f3 o, f3 d, Dda& s, Tally<COUNT>& tl)
         f3 hp;
         const bool isect = raymarch_slow<COUNT>(V, vp, dis, sg, inc, hp, tl);
         s.nanmask = (hp.x != hp.x ? 1 : 0) | (hp.y != hp.y ? 2 : 0) | (hp.z != hp.z ? 4 : 0);
-        s.ix = f2i(hp.x); s.iy = f2i(hp.y); s.iz = f2i(hp.z);
+        s.set_pos(f2i(hp.x), f2i(hp.y), f2i(hp.z));
         return isect ? DDA_HIT : DDA_NOHIT;
     }
-    s.ix = f2i(vp.x); s.iy = f2i(vp.y); s.iz = f2i(vp.z);
-    s.sx = f2i(sg.x); s.sy = f2i(sg.y); s.sz = f2i(sg.z);
+    s.set_pos(f2i(vp.x), f2i(vp.y), f2i(vp.z));
+    s.set_sign(f2i(sg.x), f2i(sg.y), f2i(sg.z));
     s.ex = sg.x * inc.x; s.ey = sg.y * inc.y; s.ez = sg.z * inc.z;
     s.dx = dis.x; s.dy = dis.y; s.dz = dis.z;
     return DDA_RUNNING;
@@ -259,32 +274,31 @@ template <bool COUNT>
 VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
 {
     // :41-42 the bounds test is implied: outside the volume the occupancy bit is the sentinel (see Volume)
-    const int key = (s.ix >> 2) + (s.iy >> 2) * V.BX + (s.iz >> 2) * V.BXY;
-    if (key != s.bkey) { s.bkey = key; s.brick = __ldg(V.bricks + key); }
-    // the voxel's bit is moved to the SIGN position (shift left by 63 - bit; the complement folds into the three LOP3 that build the
-    // index), so the test is one compare instead of AND + compare; kept opaque so that nvcc does not turn it back
-    // nbit = 63 - ((x&3) | (y&3)<<2 | (z&3)<<4) = (~x & 3) | (~y & 3)<<2 | (~z & 3)<<4, with (~v) << k written as v * -2^k - 2^k
+    // index of the brick word, counted from brick (-1,-1,-1) = the first word of the padded array, from the complemented coordinates:
+    // (ix>>2) + 1 = -(cx>>2), so index = -(cx>>2) - (cy>>4) BX - (cz>>6) BXY (nBX, nBXY are the negated strides)
+    const int key = ((s.cy >> 4) * V.nBX - (s.cx >> 2)) + (s.cz >> 6) * V.nBXY;
+    if (key != s.bkey) { s.bkey = key; s.brick = __ldg(V.bricks_top + key); }
+    // the voxel's bit is moved to the SIGN position (shift left by 63 - bit), so the test is one compare instead of AND + compare;
+    // the shift count is three masked ORs of the position words (see Dda). Kept opaque so that nvcc does not rewrite it.
     int occ;
     asm("{\n\t"
         ".reg .b64 t;\n\t"
-        ".reg .b32 lo, ty, tz, n;\n\t"
-        "mad.lo.s32 ty, %3, -4, -4;\n\t"
-        "mad.lo.s32 tz, %4, -16, -16;\n\t"
-        "lop3.b32 n, %2, 3, 0, 0x0c;\n\t"          // ~x & 3
-        "lop3.b32 n, n, 0x30, tz, 0xf8;\n\t"       // n | (0x30 & tz)
-        "lop3.b32 n, n, 0xc, ty, 0xf8;\n\t"        // n | (0xc & ty)
+        ".reg .b32 lo, n;\n\t"
+        "lop3.b32 n, %2, 3, 0, 0xc0;\n\t"          // cx & 3
+        "lop3.b32 n, %3, 0xc, n, 0xea;\n\t"        // (cy & 0xc) | n
+        "lop3.b32 n, %4, 0x30, n, 0xea;\n\t"       // (cz & 0x30) | n
         "shl.b64 t, %1, n;\n\t"
         "mov.b64 {lo, %0}, t;\n\t"
-        "}" : "=r"(occ) : "l"(s.brick), "r"(s.ix), "r"(s.iy), "r"(s.iz));
+        "}" : "=r"(occ) : "l"(s.brick), "r"(s.cx), "r"(s.cy), "r"(s.cz));
     if (occ < 0) {                                                // :44-50, or the voxel is outside: :41-42
-        const bool inside = (unsigned)s.ix < (unsigned)V.X && (unsigned)s.iy < (unsigned)V.Y && (unsigned)s.iz < (unsigned)V.Z;
+        const bool inside = (unsigned)s.ix() < (unsigned)V.X && (unsigned)s.iy() < (unsigned)V.Y && (unsigned)s.iz() < (unsigned)V.Z;
         if (inside) VT_TALLY(S, 1);
         return inside ? DDA_HIT : DDA_NOHIT;
     }
     VT_TALLY(S, 1);
     // :51 mask = step(dis.xyz, dis.yxy) * step(dis.xyz, dis.zzx)   (ties step several axes at once)
-    // Same arithmetic, instruction selection pinned: wf_trace is bound by the ALU pipe (78 % busy, profiles/r01_v6_*), so the
-    // axis masks are one 3-way minimum + three equality tests (an axis steps iff its dis IS the minimum: dis holds no NaN
+    // Same arithmetic, instruction selection pinned: wf_trace is bound by instruction issue (80 % of the slots, profiles/r02_v19_*),
+    // so the axis masks are one 3-way minimum + three equality tests (an axis steps iff its dis IS the minimum: dis holds no NaN
     // here, dda_begin) and the position updates are predicated multiply-adds, which issue on the FMA pipe.
     asm volatile("{\n\t"
                  ".reg .pred px, py, pz;\n\t"
@@ -301,8 +315,8 @@ VT_DEV int dda_step(const Volume& V, Dda& s, Tally<COUNT>& tl)
                  "@py mad.lo.s32 %1, %10, 1, %1;\n\t"
                  "@pz mad.lo.s32 %2, %11, 1, %2;\n\t"
                  "}"
-                 : "+r"(s.ix), "+r"(s.iy), "+r"(s.iz), "+f"(s.dx), "+f"(s.dy), "+f"(s.dz)
-                 : "f"(s.ex), "f"(s.ey), "f"(s.ez), "r"(s.sx), "r"(s.sy), "r"(s.sz));
+                 : "+r"(s.cx), "+r"(s.cy), "+r"(s.cz), "+f"(s.dx), "+f"(s.dy), "+f"(s.dz)
+                 : "f"(s.ex), "f"(s.ey), "f"(s.ez), "r"(s.nsx), "r"(s.nsy), "r"(s.nsz));
     return DDA_RUNNING;                                           // :38,:55 the cap cannot be reached here, see dda_begin
 }
 
@@ -387,8 +401,9 @@ VT_DEV int advance_until(float& d, float e, float tau, int nmax)
 // skip-field byte of the ray's brick (0 when the ray is outside the volume); a skip is worth trying when either level is >= 2
 VT_DEV int dda_skip_radius(const Volume& V, const Dda& s)
 {
-    if ((unsigned)s.ix >= (unsigned)V.X || (unsigned)s.iy >= (unsigned)V.Y || (unsigned)s.iz >= (unsigned)V.Z) return 0;
-    return (int)__ldg(V.skip + ((s.ix >> 2) + (s.iy >> 2) * V.SX + (s.iz >> 2) * V.SXY));
+    const int ix = s.ix(), iy = s.iy(), iz = s.iz();
+    if ((unsigned)ix >= (unsigned)V.X || (unsigned)iy >= (unsigned)V.Y || (unsigned)iz >= (unsigned)V.Z) return 0;
+    return (int)__ldg(V.skip + ((ix >> 2) + (iy >> 2) * V.SX + (iz >> 2) * V.SXY));
 }
 #ifndef VT_SKIP_MAX_ADD
 #define VT_SKIP_MAX_ADD 128
@@ -405,13 +420,14 @@ VT_DEV int dda_skip(const Volume& V, Dda& s, int v)
     const int k8 = v >> 2;
     const int shift = (k8 >= 2) ? 3 : 2, k = (k8 >= 2) ? k8 : (v & 3);
     const int cell = (1 << shift) - 1;
-    const int cx = s.ix >> shift, cy = s.iy >> shift, cz = s.iz >> shift;
+    const int ix = s.ix(), iy = s.iy(), iz = s.iz();
+    const int cx = ix >> shift, cy = iy >> shift, cz = iz >> shift;
     const int r = (k - 1) << shift;
     // steps that stay inside, per axis; at most VT_SKIP_MAX_ADD of them are taken in one go (any smaller box is as valid: the
     // additions of the whole warp run in lockstep, and one lane with a 127-step run would keep the others waiting)
-    const int nx = min(VT_SKIP_MAX_ADD, (s.sx > 0) ? min((cx << shift) + cell + r, V.X - 1) - s.ix : s.ix - max((cx << shift) - r, 0));
-    const int ny = min(VT_SKIP_MAX_ADD, (s.sy > 0) ? min((cy << shift) + cell + r, V.Y - 1) - s.iy : s.iy - max((cy << shift) - r, 0));
-    const int nz = min(VT_SKIP_MAX_ADD, (s.sz > 0) ? min((cz << shift) + cell + r, V.Z - 1) - s.iz : s.iz - max((cz << shift) - r, 0));
+    const int nx = min(VT_SKIP_MAX_ADD, s.pos_x() ? min((cx << shift) + cell + r, V.X - 1) - ix : ix - max((cx << shift) - r, 0));
+    const int ny = min(VT_SKIP_MAX_ADD, s.pos_y() ? min((cy << shift) + cell + r, V.Y - 1) - iy : iy - max((cy << shift) - r, 0));
+    const int nz = min(VT_SKIP_MAX_ADD, s.pos_z() ? min((cz << shift) + cell + r, V.Z - 1) - iz : iz - max((cz << shift) - r, 0));
     if (min(nx, min(ny, nz)) < 3) return 0;
     // first value at which axis a would step OUT of the box: D_a(n_a) ~ d_a + n_a e_a; stay 0.1 % below the smallest
     const float tau = gmin(s.dx + (float)nx * s.ex, gmin(s.dy + (float)ny * s.ey, s.dz + (float)nz * s.ez)) * 0.999f;
@@ -445,7 +461,7 @@ VT_DEV int dda_skip(const Volume& V, Dda& s, int v)
     }
     if (!done) return 0;
     s.dx = dx; s.dy = dy; s.dz = dz;
-    s.ix += s.sx * kx; s.iy += s.sy * ky; s.iz += s.sz * kz;
+    s.advance(kx, ky, kz);
     return kx + ky + kz;
 }
 

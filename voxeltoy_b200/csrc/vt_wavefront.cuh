@@ -152,7 +152,7 @@ VT_DEV int2 wf_rng_unpack(const Frame& F, int idx)
 // flags of a finished traversal (dda.h:63-79)
 VT_DEV int wf_hit_flags(int status, const Dda& s)
 {
-    const bool ground = (status != DDA_HIT) && !(s.nanmask & 2) && (s.iy < 0);       // dda.h:75-78
+    const bool ground = (status != DDA_HIT) && !(s.nanmask & 2) && (s.iy() < 0);     // dda.h:75-78
     return (status == DDA_HIT ? WF_HIT_VOXEL : (ground ? WF_HIT_GROUND : 0)) | (s.nanmask << WF_HIT_NAN_SHIFT);
 }
 // pathTracer.fs:134-153: is the sampled light visible, given the end of the shadow traversal
@@ -161,7 +161,7 @@ VT_DEV int wf_light_visible(const Volume& V, int target, int status, const Dda& 
     const int flags = wf_hit_flags(status, s);
     if (target < 0) return (flags & 3) == 0;                                            // environment: nothing in the way
     // emissive voxel: the traversal must end on exactly that voxel (a ground or NaN position never equals it)
-    return status == DDA_HIT && (flags >> WF_HIT_NAN_SHIFT) == 0 && (s.ix + s.iy * V.X + s.iz * V.X * V.Y) == target;
+    return status == DDA_HIT && (flags >> WF_HIT_NAN_SHIFT) == 0 && (s.ix() + s.iy() * V.X + s.iz() * V.X * V.Y) == target;
 }
 
 // Where does a path go whose primary / bounce ray has just ended (pathTracer.fs:202-208, :214, :282-291)? Surface hit with
@@ -176,15 +176,15 @@ VT_DEV int wf_route(const Volume& V, const Frame& F, int flags, int bounces, int
 VT_DEV int4 wf_entry(unsigned int slot, const Dda& s, int flags, unsigned int pid)
 {
     // a NaN component holds cvt.rzi(NaN) = 0; finite components stay within [-1, res] (a step moves one voxel): 16 bits each
-    return make_int4((int)slot, wf_pack16(s.ix, s.iy), wf_pack16(s.iz, flags), (int)pid);
+    return make_int4((int)slot, wf_pack16(s.ix(), s.iy()), wf_pack16(s.iz(), flags), (int)pid);
 }
 
 VT_DEV void wf_store_ray(const WfState& S, int region, unsigned int slot, int status, const Dda& s, int kind, int bounces, int aux, int rngw)
 {
     const size_t at = (size_t)slot + (region ? (size_t)S.rq_cap : 0);
-    st_stream16(S.rq_a + at, make_int4(wf_pack16(s.ix, s.iy), (s.iz & 0xffff) | (kind << 16) | (status << 18) | (s.nanmask << 20) | (bounces << 23), aux, rngw));
-    st_stream16(S.rq_b + at, make_float4(s.dx, s.dy, s.dz, s.sx < 0 ? -s.ex : s.ex));     // |1/d| > 0 (dda_begin): the sign bit is free
-    st_stream8(S.rq_c + at, make_float2(s.sy < 0 ? -s.ey : s.ey, s.sz < 0 ? -s.ez : s.ez));
+    st_stream16(S.rq_a + at, make_int4(wf_pack16(s.ix(), s.iy()), (s.iz() & 0xffff) | (kind << 16) | (status << 18) | (s.nanmask << 20) | (bounces << 23), aux, rngw));
+    st_stream16(S.rq_b + at, make_float4(s.dx, s.dy, s.dz, s.pos_x() ? s.ex : -s.ex));     // |1/d| > 0 (dda_begin): the sign bit is free
+    st_stream8(S.rq_c + at, make_float2(s.pos_y() ? s.ey : -s.ey, s.pos_z() ? s.ez : -s.ez));
 }
 
 // Slot reservation in the next generation, aggregated lanes -> warp (ballot) -> CTA (shared-memory atomic) -> one global
@@ -309,8 +309,8 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
         f3 ro = mk3(0.f), rd = mk3(0.f);
         int2 rng = make_int2(0, 0);
         Dda s;
-        s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.steps = 0; s.bkey = -1; s.brick = 0ull;
-        s.sx = s.sy = s.sz = 1; s.dx = s.dy = s.dz = s.ex = s.ey = s.ez = 0.f;
+        s.set_pos(0, 0, 0); s.nanmask = 0; s.steps = 0; s.bkey = kNoBrick; s.brick = 0ull;
+        s.set_sign(1, 1, 1); s.dx = s.dy = s.dz = s.ex = s.ey = s.ez = 0.f;
         if (mine) {
             valid = true;
             const int sample = L.first_sample + (pass0 + pass_local) * L.sample_stride;
@@ -359,7 +359,7 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
         int q = 0, flags = 0;
         if (valid) {
             flags = wf_hit_flags(status, s) | WF_HIT_PRIMARY;
-            q = wf_route(V, F, flags, -1, s.ix, s.iy, s.iz);
+            q = wf_route(V, F, flags, -1, s.ix(), s.iy(), s.iz());
         }
         unsigned int slot, qpos;
         wf_reserve_slot_and_queue(cnt, cnt + 1, valid, q, sm, slot, qpos);
@@ -417,8 +417,8 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S,
     constexpr int kChunk = (SKIP && !COUNT) ? kWfStepChunkSkip : kWfStepChunk;
     const int chunk_guard = (V.X + V.Y + V.Z) / kChunk + 8;         // belt and braces: see dda_begin on why rays always leave
     Dda s;
-    s.ix = s.iy = s.iz = 0; s.nanmask = 0; s.steps = 0; s.bkey = -1; s.brick = 0ull;
-    s.dx = s.dy = s.dz = 0.f; s.ex = s.ey = s.ez = 0.f; s.sx = s.sy = s.sz = 1;
+    s.set_pos(0, 0, 0); s.nanmask = 0; s.steps = 0; s.bkey = kNoBrick; s.brick = 0ull;
+    s.dx = s.dy = s.dz = 0.f; s.ex = s.ey = s.ez = 0.f; s.set_sign(1, 1, 1);
 
     // routes up to 32 parked paths at full width: looks at the ray record again (kind, bounce count, path id, rng word), finds
     // the queue (pathTracer.fs:202-208, :214, :282-291) and appends the entries; slots are reserved per warp in chunks
@@ -487,10 +487,10 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S,
                     const size_t at = r < n ? (size_t)r : (size_t)(r - n) + (size_t)S.rq_cap;
                     const int4 a = S.rq_a[at];                           // re-read at retire: default caching
                     const float4 b = ld_stream16(S.rq_b + at); const float2 c = ld_stream8(S.rq_c + at);
-                    s.ix = wf_lo16(a.x); s.iy = wf_hi16(a.x); s.iz = wf_lo16(a.y);
+                    s.set_pos(wf_lo16(a.x), wf_hi16(a.x), wf_lo16(a.y));
                     s.dx = b.x; s.dy = b.y; s.dz = b.z; s.ex = gabs(b.w); s.ey = gabs(c.x); s.ez = gabs(c.y);
-                    s.sx = f2bits(b.w) < 0 ? -1 : 1; s.sy = f2bits(c.x) < 0 ? -1 : 1; s.sz = f2bits(c.y) < 0 ? -1 : 1;
-                    s.steps = 0; s.bkey = -1;
+                    s.set_sign(f2bits(b.w) < 0 ? -1 : 1, f2bits(c.x) < 0 ? -1 : 1, f2bits(c.y) < 0 ? -1 : 1);
+                    s.steps = 0; s.bkey = kNoBrick;
                     status = (a.y >> 18) & 3;                            // DDA_RUNNING, or the final status dda_begin found
                     guard = chunk_guard;
                     w = r;
@@ -542,7 +542,7 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S,
                 if (F.n_emissive == 0) {
                     // towards the environment (the only light there is): visible iff nothing was hit, the virtual ground included
                     // (a NaN height is stored as 0, so the ground test needs no NaN mask). No second look at the record.
-                    if (status != DDA_HIT && !(s.iy < 0)) atomicOr(vis + (w >> 5), 1u << (w & 31));
+                    if (status != DDA_HIT && !(s.iy() < 0)) atomicOr(vis + (w >> 5), 1u << (w & 31));
                 } else {
                     const int4 a = S.rq_a[w];                           // light target; NaN mask of a ray resolved by dda_begin
                     s.nanmask = (a.y >> 20) & 7;
@@ -551,7 +551,7 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S,
                 }
             } else {                                   // bounce / primary ray: parked, routed later at full width
                 park = true;
-                p_slot = w - n; p_xy = wf_pack16(s.ix, s.iy); p_zs = (s.iz & 0xffff) | (status << 16);
+                p_slot = w - n; p_xy = wf_pack16(s.ix(), s.iy()); p_zs = (s.iz() & 0xffff) | (status << 16);
             }
             have = false;
         }
@@ -647,7 +647,7 @@ wf_shade_kernel(const Volume V, const Frame F, const WfState S, const int gen, W
         float4 o0, o1, o2, o3;
         o0 = o1 = o2 = o3 = make_float4(0.f, 0.f, 0.f, 0.f);
         Dda sa, sb;
-        sa.ix = sa.iy = sa.iz = 0; sa.nanmask = 0; sa.sx = sa.sy = sa.sz = 1; sa.dx = sa.dy = sa.dz = sa.ex = sa.ey = sa.ez = 0.f;
+        sa.set_pos(0, 0, 0); sa.nanmask = 0; sa.set_sign(1, 1, 1); sa.dx = sa.dy = sa.dz = sa.ex = sa.ey = sa.ez = 0.f;
         sb = sa;
         if (valid) {
             const unsigned int slot = (unsigned)e.x;
