@@ -396,7 +396,20 @@ def run_config(args, name, scaling, passes, steps, warmup, rank, world, local_ra
     for i in range(n_count):
         r.renderPasses(local_passes)
     ctx.sync()
-    cnt = ctx.counters(); ctx.counters_enable(False)
+    cnt = ctx.counters()
+    # the same sample indices again with no bounce: what is left is the primary traversal, which wf_generate performs; the
+    # difference is the work of wf_trace alone
+    primary_steps = 0
+    try:
+        r.setRenderSettings(maxBounces=0)
+        r.resetRender(); ctx.reset_counters()
+        for i in range(n_count):
+            r.renderPasses(local_passes)
+        ctx.sync()
+        primary_steps = ctx.counters()["dda_steps"]
+    finally:
+        ctx.counters_enable(False)
+        r.setRenderSettings(maxBounces=c["bounces"]); r.resetRender()
     share = (1.0 / world) if mode == vtgroup.PART_TILES and world > 1 else 1.0
     n_samp = float(npx) * local_passes * n_count * share               # samples THIS rank rendered in the replay
     cnt = dict(cnt); cnt["paths"] = n_samp
@@ -448,12 +461,16 @@ def run_config(args, name, scaling, passes, steps, warmup, rank, world, local_ra
     # issues 4 warp instructions per clock
     sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
-    trace_ms = ktimes["trace"][0] + ktimes.get("generate", (0.0, 0))[0]   # the primary rays are traced inside wf_generate
     issue_peak = sms * 4 * sm_hz / 25.0 * 32.0
-    issue_achieved = cnt["dda_steps"] / n_count * steps / (trace_ms * 1e-3) if trace_ms > 0 else 0.0
-    roof["issue"] = {"kernel": "wf_trace_kernel + wf_generate_kernel (which traces the primary rays; its ray set-up time is included, so the figure is conservative)", "achieved": issue_achieved / 1e9, "peak": issue_peak / 1e9, "unit": "G DDA iterations/s",
-                     "frac": issue_achieved / issue_peak,
-                     "how": "counted DDA iterations / device time of wf_trace + wf_generate vs SMs x 4 issue slots x SM clock / 25 instructions per iteration x 32 lanes"}
+
+    def issue(kernel, steps_counted, ms, how):
+        ach = steps_counted / n_count * steps / (ms * 1e-3) if ms > 0 else 0.0
+        return {"kernel": kernel, "achieved": ach / 1e9, "peak": issue_peak / 1e9, "unit": "G DDA iterations/s", "frac": ach / issue_peak, "how": how}
+    roof["issue"] = issue("wf_trace_kernel", cnt["dda_steps"] - primary_steps, ktimes["trace"][0],
+                          "DDA iterations of the shadow + bounce rays (counted replay minus a counted 0-bounce replay of the same samples) / device time "
+                          "of wf_trace vs SMs x 4 issue slots x SM clock / 25 instructions per iteration x 32 lanes")
+    roof["issue_primary"] = issue("wf_generate_kernel", primary_steps, ktimes.get("generate", (0.0, 0))[0],
+                                  "DDA iterations of the primary rays / device time of wf_generate (which also sets the rays up: conservative), same ceiling")
     roof["note"] = "both big kernels are issue / latency bound, not bandwidth bound: see profiles/ (issue slots busy, lanes per instruction)"
     out["roofline"] = roof
     if grp is not None:
