@@ -765,7 +765,8 @@ static int wf_reserve(vt_ctx* c, int lane, size_t n_paths, int n_iters)
         VT_CUDA(c, cudaEventCreateWithFlags(&c->wf_acc[lane], cudaEventDisableTiming));
         if (!c->wf_fork) VT_CUDA(c, cudaEventCreateWithFlags(&c->wf_fork, cudaEventDisableTiming));
     }
-    if (n_paths > c->wf_capacity[lane]) {
+    if (n_paths > c->wf_capacity[lane] || c->wf_queue_slack > c->wf_slack_alloc[lane]) {
+        n_paths = std::max(n_paths, c->wf_capacity[lane]);
         VT_CUDA(c, cudaDeviceSynchronize());
         cudaFree(c->d_wf_pool[lane]); c->d_wf_pool[lane] = nullptr; c->wf_capacity[lane] = 0;
         const size_t n_pad = (n_paths + 63) & ~(size_t)63;                  // keeps every sub-array 256-byte aligned
@@ -781,7 +782,7 @@ static int wf_reserve(vt_ctx* c, int lane, size_t n_paths, int n_iters)
         W.samples = (float4*)take(n_pad * 16);
         for (int k = 0; k < kWfQueues; ++k) { W.sq[k] = (int4*)take(n_queue * 16); W.sq_rng[k] = (int*)take(n_queue * 4); }
         W.vis = (unsigned int*)take(((n_pad + 2047) / 2048) * 256);
-        c->wf_capacity[lane] = n_paths;
+        c->wf_capacity[lane] = n_paths; c->wf_slack_alloc[lane] = c->wf_queue_slack;
     }
     if (n_iters > c->wf_counts_cap[lane]) {
         VT_CUDA(c, cudaDeviceSynchronize());
@@ -815,8 +816,12 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
         c->wf_sms = std::max(1, sms);
     }
     // every trace warp can leave one partly filled chunk per queue behind (COUNT and plain builds may differ in occupancy)
-    c->wf_queue_slack = std::max(c->wf_queue_slack, (size_t)c->wf_trace_blocks[ci] * (kWfTraceThreads / 32) * kWfQueueChunk + 4096);
     const int n_items = my_tiles * kTile * kTile;
+    // every warp that appends to the shade queues can leave one partly filled chunk per queue behind: the warps of wf_trace (COUNT and
+    // plain builds may differ in occupancy) and those of wf_generate (one per 32 pixels and thread row)
+    const int gen_x = n_items / 256, gen_rows_max = std::max(1, (std::max(1, c->wf_sms) * 8 + gen_x - 1) / gen_x);
+    c->wf_queue_slack = std::max(c->wf_queue_slack, (size_t)c->wf_trace_blocks[ci] * (kWfTraceThreads / 32) * kWfQueueChunk + 4096);
+    c->wf_queue_slack = std::max(c->wf_queue_slack, (size_t)gen_x * gen_rows_max * (256 / 32) * kWfQueueChunk + 4096);
     // split the passes of this call into batches: at most wf_max_paths paths in flight over all lanes, and at least
     // `lanes` batches when there are enough passes, so that two batches always overlap
     const int lanes = std::max(1, std::min(c->wf_lanes, L.n_passes));
@@ -859,7 +864,7 @@ static int wf_render(vt_ctx* c, const Volume& V, const Frame& F, const RenderLau
         if (batch >= lanes) VT_CUDA(c, cudaStreamWaitEvent(st, c->wf_acc[lane], 0));      // the lane's samples were folded in
         VT_CUDA(c, cudaMemsetAsync(cn, 0, sizeof(WfCounts) * (size_t)n_iters, st));
         { WfTimer t(c, VT_K_GENERATE, st);
-          const int gen_x = n_items / 256, gen_rows = std::min(nb, std::max(1, (c->wf_sms * 8 + gen_x - 1) / gen_x));   // enough CTAs for every SM, else 1 row
+          const int gen_rows = std::min(nb, gen_rows_max);   // enough CTAs for every SM, else 1 row
           const dim3 gg((unsigned)gen_x, (unsigned)gen_rows);
           if (V.skip != nullptr && !COUNT) wf_generate_kernel<COUNT, true><<<gg, 256, 0, st>>>(V, F, L, S, pass0, nb, cn, prim, c->d_counters);
           else wf_generate_kernel<COUNT, false><<<gg, 256, 0, st>>>(V, F, L, S, pass0, nb, cn, prim, c->d_counters); }

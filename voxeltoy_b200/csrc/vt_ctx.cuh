@@ -70,7 +70,8 @@ struct vt_ctx {
     cudaStream_t wf_stream[kWfLanes] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t wf_fork = nullptr, wf_done[kWfLanes] = {nullptr, nullptr, nullptr, nullptr}, wf_acc[kWfLanes] = {nullptr, nullptr, nullptr, nullptr};
     size_t wf_max_paths = (size_t)128 << 20;   // paths in flight per batch: 324 B each -> <= 43.5 GB of the 180 GB (C2, round 1: 32 -> 64 -> 128 Mi = 2 542 -> 2 582 -> 2 607 Msamples/s)
-    size_t wf_queue_slack = 0;                 // queue entries beyond the path count: the chunked reservations of wf_trace
+    size_t wf_queue_slack = 0;                 // queue entries beyond the path count: the chunked reservations of wf_trace and wf_generate
+    size_t wf_slack_alloc[kWfLanes] = {0, 0, 0, 0};   // the slack each lane's pool was allocated with
     int wf_shade_blocks[2] = {0, 0}, wf_trace_blocks[2] = {0, 0}, wf_sms = 0;
     // per-kernel device timing (vt_kernel_timing_enable): event pairs around every wavefront launch
     bool timing = false;

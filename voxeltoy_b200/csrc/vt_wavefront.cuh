@@ -216,39 +216,49 @@ VT_DEV unsigned int wf_reserve_slot(WfCounts* __restrict__ cnt, bool want, WfBlo
     return sm.base + wt + (unsigned)__popc(mt & lt);
 }
 
-// wf_generate: one slot of generation 0 and one position in the shade queue `q` per thread with `want`, aggregated the same way
-// (counter 0 = slots, counters 1..5 = the queues; lanes 0..5 of a warp each carry one counter through the shared-memory stage).
-struct WfBlockCounters6 { unsigned int cnt[1 + kWfQueues], base[1 + kWfQueues]; };
-VT_DEV void wf_reserve6_init(WfBlockCounters6& sm)
-{
-    if (threadIdx.x < 1 + kWfQueues) sm.cnt[threadIdx.x] = 0u;
-    __syncthreads();
-}
-VT_DEV void wf_reserve_slot_and_queue(WfCounts* __restrict__ cnt, WfCounts* __restrict__ cq, bool want, int q, WfBlockCounters6& sm,
-                                      unsigned int& slot, unsigned int& qpos)
+// Appends one queue entry per lane with q >= 0 to shade queue q. Positions are reserved per WARP in chunks of kWfQueueChunk
+// entries (one global atomic per chunk, no CTA barrier): cur_next / cur_end = this warp's [next, end) per queue (shared memory,
+// warp-uniform, touched by lane 0); the old chunk is filled up first, the rest opens a new one. ALL lanes of the warp must call.
+VT_DEV void wf_append_entries(const WfState& S, WfCounts* __restrict__ cq, unsigned int* cur_next, unsigned int* cur_end,
+                              int q, int4 entry, int rngw)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const unsigned mv = __ballot_sync(full, want);
-    unsigned mine = 0u, carried = (lane == 0) ? mv : 0u;               // mask of the lanes that share my queue / of the counter this lane carries
+    unsigned pending = __ballot_sync(full, q >= 0);
+    while (pending != 0u) {                                     // one round per queue present: usually one or two
+        const int k = __shfl_sync(full, q, __ffs(pending) - 1);
+        const unsigned m = __ballot_sync(full, q == k);
+        pending &= ~m;
+        const unsigned cnt_k = (unsigned)__popc(m);
+        const unsigned nx = cur_next[k], avail = cur_end[k] - nx;
+        unsigned base2 = 0;
+        if (avail < cnt_k) {
+            if (lane == 0) base2 = atomicAdd(&cq->sq[k], (unsigned)kWfQueueChunk);
+            base2 = __shfl_sync(full, base2, 0);
+        }
+        if (q == k) {
+            const unsigned rank = (unsigned)__popc(m & lt);
+            const unsigned dst = rank < avail ? nx + rank : base2 + (rank - avail);
+            st_stream16(S.sq[k] + dst, entry); st_stream4(S.sq_rng[k] + dst, rngw);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (avail < cnt_k) { cur_next[k] = base2 + (cnt_k - avail); cur_end[k] = base2 + (unsigned)kWfQueueChunk; }
+            else cur_next[k] = nx + cnt_k;
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+}
+// the unused tail of the warp's chunks: marked invalid (wf_shade skips such entries)
+VT_DEV void wf_invalidate_tails(const WfState& S, const unsigned int* cur_next, const unsigned int* cur_end)
+{
+    const int lane = threadIdx.x & 31;
     #pragma unroll
-    for (int k = 0; k < kWfQueues; ++k) {
-        const unsigned m = __ballot_sync(full, want && q == k);
-        if (want && q == k) mine = m;
-        if (lane == 1 + k) carried = m;
-    }
-    unsigned int wb = 0;
-    if (lane < 1 + kWfQueues && carried != 0u) wb = atomicAdd(&sm.cnt[lane], (unsigned)__popc(carried));
-    const unsigned int wb_slot = __shfl_sync(full, wb, 0), wb_q = __shfl_sync(full, wb, want ? 1 + q : 0);
-    __syncthreads();
-    if (threadIdx.x < 1 + kWfQueues && sm.cnt[threadIdx.x] != 0u) {
-        sm.base[threadIdx.x] = atomicAdd(threadIdx.x == 0 ? &cnt->tq : &cq->sq[threadIdx.x - 1], sm.cnt[threadIdx.x]);
-        sm.cnt[threadIdx.x] = 0u;                                       // ready for the next call (visible after the barrier below)
-    }
-    __syncthreads();
-    slot = sm.base[0] + wb_slot + (unsigned)__popc(mv & lt);
-    qpos = want ? sm.base[1 + q] + wb_q + (unsigned)__popc(mine & lt) : 0u;
+    for (int k = 0; k < kWfQueues; ++k)
+        for (unsigned i = cur_next[k] + (unsigned)lane; i < cur_end[k]; i += 32u)
+            S.sq[k][i] = make_int4((int)kWfInvalid, 0, 0, 0);
 }
 
 template <bool COUNT>
@@ -289,9 +299,12 @@ VT_GLOBAL void __launch_bounds__(256, VT_WF_GENERATE_MIN_BLOCKS)
 wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const WfState S, int pass0, int n_batch,
                    WfCounts* __restrict__ cnt, int* __restrict__ primary, Counters* __restrict__ counters)
 {
-    __shared__ WfBlockCounters6 sm;
-    wf_reserve6_init(sm);
+    // per-warp cursors into the shade queues, as in wf_trace
+    __shared__ unsigned int cur_next[256 / 32][kWfQueues], cur_end[256 / 32][kWfQueues];
     const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) < kWfQueues) { cur_next[warp][threadIdx.x & 31] = 0u; cur_end[warp][threadIdx.x & 31] = 0u; }
+    __syncwarp();
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     Tally<COUNT> tl; tl.clear();
     int px = 0, py = 0;
@@ -355,22 +368,21 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
                 }
             }
         }
-        // ---- routing (:202-208, :214): one slot of generation 0 and one shade-queue entry per path ---------------------
-        int q = 0, flags = 0;
+        // ---- routing (:202-208, :214): one shade-queue entry per path. The slot of a generation-0 path is its path id: no
+        // reservation, no CTA barrier (the barriers of a CTA-wide reservation were 12 % of this kernel's stall samples,
+        // profiles/r02_v21_wf_generate_*), and the records of a warp are written side by side. Nothing walks generation 0 by
+        // slot -- wf_shade reaches its records through the queue entries -- so the slots of sky pixels simply stay unused.
+        int q = -1, flags = 0;
         if (valid) {
             flags = wf_hit_flags(status, s) | WF_HIT_PRIMARY;
             q = wf_route(V, F, flags, -1, s.ix(), s.iy(), s.iz());
-        }
-        unsigned int slot, qpos;
-        wf_reserve_slot_and_queue(cnt, cnt + 1, valid, q, sm, slot, qpos);
-        if (valid) {
             // a primary path has radiance 0, throughput 1, nothing pending, bounce 0, no BSDF pdf: wf_shade synthesises all of that
             // from the PRIMARY flag, and only the first sector of the record is written
-            st_stream32(S.state[0] + 4 * (size_t)slot, make_float4(ro.x, ro.y, ro.z, rd.x), make_float4(rd.y, rd.z, 0.0f, 0.0f));
-            st_stream16(S.sq[q] + qpos, wf_entry(slot, s, flags, pid));
-            st_stream4(S.sq_rng[q] + qpos, wf_rng_pack(F, rng));
+            st_stream32(S.state[0] + 4 * (size_t)pid, make_float4(ro.x, ro.y, ro.z, rd.x), make_float4(rd.y, rd.z, 0.0f, 0.0f));
         }
+        wf_append_entries(S, cnt + 1, cur_next[warp], cur_end[warp], q, wf_entry(pid, s, flags, pid), wf_rng_pack(F, rng));
     }
+    wf_invalidate_tails(S, cur_next[warp], cur_end[warp]);
     wf_flush_tally<COUNT>(tl, counters);
 }
 
@@ -442,31 +454,7 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S,
         }
         park_head = (park_head + nf) & (kWfPark - 1); park_cnt -= nf;
         // routed paths -> shade queues, slots reserved per warp in chunks
-        unsigned pending = __ballot_sync(full, q >= 0);
-        while (pending != 0u) {                                     // one round per queue present: usually one or two
-            const int k = __shfl_sync(full, q, __ffs(pending) - 1);
-            const unsigned m = __ballot_sync(full, q == k);
-            pending &= ~m;
-            const unsigned cnt_k = (unsigned)__popc(m);
-            const unsigned nx = cur_next[warp][k], avail = cur_end[warp][k] - nx;
-            unsigned base2 = 0;
-            if (avail < cnt_k) {                                    // the old chunk is filled up first, the rest opens a new one
-                if (lane == 0) base2 = atomicAdd(&cnext->sq[k], (unsigned)kWfQueueChunk);
-                base2 = __shfl_sync(full, base2, 0);
-            }
-            if (q == k) {
-                const unsigned rank = (unsigned)__popc(m & lt);
-                const unsigned dst = rank < avail ? nx + rank : base2 + (rank - avail);
-                st_stream16(S.sq[k] + dst, entry); st_stream4(S.sq_rng[k] + dst, rngw);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                if (avail < cnt_k) { cur_next[warp][k] = base2 + (cnt_k - avail); cur_end[warp][k] = base2 + (unsigned)kWfQueueChunk; }
-                else cur_next[warp][k] = nx + cnt_k;
-            }
-            __syncwarp();
-        }
-        __syncwarp();
+        wf_append_entries(S, cnext, cur_next[warp], cur_end[warp], q, entry, rngw);
     };
 
     for (;;) {
@@ -568,11 +556,7 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S,
         if (park_cnt >= 32u) route_parked();
     }
     if (park_cnt != 0u) route_parked();
-    // the unused tail of the warp's chunks: marked invalid (wf_shade skips such entries)
-    #pragma unroll
-    for (int k = 0; k < kWfQueues; ++k)
-        for (unsigned i = cur_next[warp][k] + (unsigned)lane; i < cur_end[warp][k]; i += 32u)
-            S.sq[k][i] = make_int4((int)kWfInvalid, 0, 0, 0);
+    wf_invalidate_tails(S, cur_next[warp], cur_end[warp]);
 #ifdef VT_SKIP_STATS
     if (SKIP) { atomicAdd(&counters->E, dbg_calls); atomicAdd(&counters->Q, dbg_ok); atomicAdd(&counters->H, dbg_steps); atomicAdd(&counters->S, dbg_plain); atomicAdd(&counters->R, dbg_long); }
 #endif
