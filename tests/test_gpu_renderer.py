@@ -99,6 +99,17 @@ def test_renderer_c2_flow_env_thin_lens_autofocus(renderer, tmp_path):
     raw = open(ppm, "rb").read()
     head = b"P6\n240 136\n255\n"
     assert raw.startswith(head) and np.array_equal(np.frombuffer(raw[len(head):], np.uint8).reshape(136, 240, 3), want[::-1, :, :3])
+    # OpenEXR keeps the floats (FLOAT channels, ZIP), top row first; and the written file is itself a valid environment map
+    exr = str(tmp_path / "o.exr")
+    r.saveImage(exr)
+    assert util.same_bits(vt.host.load_image(exr), got[::-1, :, :3]).all()
+    pfm_env = str(tmp_path / "env.pfm")
+    vt.host.write_pfm(pfm_env, np.nan_to_num(got[::-1, :, :3], nan=0.0))
+    r.setRenderSettings(backgroundImage=pfm_env); r.resetRender(); r.renderPasses(2); from_pfm = r.context().read_average()
+    exr_env = str(tmp_path / "env.exr")
+    vt.host.write_exr(exr_env, np.nan_to_num(got[::-1, :, :3], nan=0.0))
+    r.setRenderSettings(backgroundImage=exr_env); r.resetRender(); r.renderPasses(2)
+    assert util.same_bits(r.context().read_average(), from_pfm).all()             # same pixels in, same frame out
 
 
 def test_renderer_mesh_tools_and_edit_flow(renderer):

@@ -19,7 +19,7 @@ def main():
     for spec in sys.argv[1:]:
         name, _, flags = spec.partition(":")
         lib = os.path.join(out_dir, name + ".so")
-        cmd = ["nvcc"] + vb.NVCC_FLAGS + [f for f in flags.split(",") if f] + ["-I", os.path.join(vb.ROOT, "include"), "-I", vb.HERE, "-o", lib] + cus + cpps
+        cmd = ["nvcc"] + vb.NVCC_FLAGS + [f for f in flags.split(",") if f] + ["-I", os.path.join(vb.ROOT, "include"), "-I", vb.HERE, "-o", lib] + cus + cpps + ["-lz"]
         procs.append((name, subprocess.Popen(cmd)))
     for name, p in procs:
         if p.wait() != 0:

@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
         cus = _sources(CSRC, (".cu",))
         cpps = _sources(HOST, (".cpp",))
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(ROOT, "include"), "-I", HERE,
-                                                                            "-o", lib] + cus + cpps
+                                                                            "-o", lib] + cus + cpps + ["-lz"]
         subprocess.check_call(cmd)
     # the C++ multi-GPU demo (tools/vt_group_demo.cpp): a host program without Python over the same library
     demo_src = os.path.join(ROOT, "tools", "vt_group_demo.cpp")

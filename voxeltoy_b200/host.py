@@ -71,6 +71,7 @@ _SIG = {
     "vth_widget_run_script": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_int]), "vth_widget_pump": (C.c_int, [P, C.c_int]),
     "vth_widget_update_pending": (C.c_int, [P]), "vth_widget_paints": (C.c_ulong, [P]),
     "vth_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint, C.c_uint]),
+    "vth_write_exr": (C.c_int, [C.c_char_p, f32p, C.c_uint, C.c_uint, C.c_int]),
     "vth_load_image_dims": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "vth_load_image": (C.c_int, [C.c_char_p, f32p]),
 }
@@ -207,7 +208,16 @@ def write_pfm(path, rgb):
         raise IOError("cannot write " + path)
 
 
+def write_exr(path, pixels):
+    """writeEXR (host/image_formats.cpp): (h, w, 3 or 4) float32, rows top-down -> FLOAT channels, ZIP compression"""
+    pixels = np.ascontiguousarray(pixels, np.float32)
+    assert pixels.ndim == 3 and pixels.shape[2] in (3, 4)
+    if lib().vth_write_exr(path.encode(), _fp(pixels), pixels.shape[1], pixels.shape[0], pixels.shape[2]) != 0:
+        raise IOError("cannot write " + path)
+
+
 def load_image(path):
+    """loadImage (renderer/image.cpp:28-59): .pfm, .hdr (RGBE), .exr and .png -> (h, w, 3) float32, row 0 = top"""
     w = C.c_uint(); h = C.c_uint()
     if lib().vth_load_image_dims(path.encode(), C.byref(w), C.byref(h)) != 0:
         raise IOError("cannot read " + path)

@@ -1,7 +1,7 @@
 // image.cpp -- environment-map ingest and the marginal / conditional CDF construction used to importance-sample
 // it (PBRT-2 14.6.5). calculateCDF follows renderer/image.cpp:68-283 and :349-389 of the reference. The reference
 // delegates file I/O, down-scaling, luminance and the 3x3 blur to OpenImageIO (un-vendored, un-pinned: SURVEY 8c);
-// this build owns that chain: PFM / Radiance-HDR readers, box down-scale to <= 512, Rec.709 luminance, separable
+// this build owns that chain: PFM / Radiance-HDR readers here, OpenEXR / PNG in image_formats.cpp, area-weighted down-scale to <= 512, Rec.709 luminance, separable
 // [1 2 1]/4 blur with clamped edges.
 #include "vt_host.h"
 
@@ -86,6 +86,8 @@ bool loadImage(const std::string& path, unsigned int& outWidth, unsigned int& ou
     if (c0 == 'P' && (c1 == 'F' || c1 == 'f')) ok = readPFM(fp, outWidth, outHeight, outPixelData);
     else if (c0 == '#' && c1 == '?') ok = readHDR(fp, outWidth, outHeight, outPixelData);
     fclose(fp);
+    if (c0 == 0x76 && c1 == 0x2f) return readEXR(path, outWidth, outHeight, outPixelData);       // OpenEXR magic 76 2f 31 01
+    if (c0 == 0x89 && c1 == 'P') return readPNG(path, outWidth, outHeight, outPixelData);
     return ok;
 }
 

@@ -7,7 +7,7 @@
 //     compression NONE, RLE, ZIPS and ZIP (file layout: openexr.com "OpenEXR File Layout"); written as FLOAT + ZIP.
 //     Tiled, deep and multi-part files and the PIZ / PXR24 / B44 / DWA codecs are refused with a message.
 //   * PNG (RFC 2083): 8 / 16-bit grey, grey + alpha, RGB, RGBA and 1..8-bit palette images, non-interlaced -- the reference's own
-//     resources/*.png are of that kind. Samples map to floats as OpenImageIO does: v / (2^bits - 1), no transfer function.
+//     resources/*.png are of that kind. Samples map to floats as OpenImageIO does: v * (1 / (2^bits - 1)), no transfer function.
 #include "vt_host.h"
 
 #include <zlib.h>
@@ -351,7 +351,7 @@ bool readPNG(const std::string& path, unsigned int& outWidth, unsigned int& outH
             }
             if (ctype == 3) {
                 const size_t e = (size_t)v[0] * 3;
-                if (e + 2 < plte.size()) { dst[3 * x] = plte[e] / 255.0f; dst[3 * x + 1] = plte[e + 1] / 255.0f; dst[3 * x + 2] = plte[e + 2] / 255.0f; }
+                if (e + 2 < plte.size()) { const float s8 = 1.0f / 255.0f; dst[3 * x] = plte[e] * s8; dst[3 * x + 1] = plte[e + 1] * s8; dst[3 * x + 2] = plte[e + 2] * s8; }
             } else if (comps <= 2) { dst[3 * x] = dst[3 * x + 1] = dst[3 * x + 2] = (float)v[0] * scale; }
             else { dst[3 * x] = (float)v[0] * scale; dst[3 * x + 1] = (float)v[1] * scale; dst[3 * x + 2] = (float)v[2] * scale; }
         }

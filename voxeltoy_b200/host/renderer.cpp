@@ -314,6 +314,12 @@ void Renderer::saveImage(const std::string& file)                               
     }
     std::vector<float> pixels((size_t)xres * yres * 4);
     if (!readAverage(&pixels[0])) return;
+    if (ext == ".exr") {                                                       // float RGBA, rows top-down: the flip of :1131-1136 on the host
+        std::vector<float> top((size_t)xres * yres * 4);
+        for (int y = 0; y < yres; ++y) memcpy(&top[(size_t)y * xres * 4], &pixels[(size_t)(yres - 1 - y) * xres * 4], (size_t)xres * 4 * sizeof(float));
+        if (!writeEXR(file, &top[0], xres, yres, 4)) log("could not write " + file);
+        return;
+    }
     FILE* fp = fopen(file.c_str(), "wb");
     if (!fp) return;
     fprintf(fp, "PF\n%d %d\n-1.0\n", xres, yres);                              // PFM stores bottom-to-top = GL order
