@@ -53,6 +53,29 @@ def test_many_passes_continue_the_running_average(vt_ctx):
     assert util.same_bits(vt_ctx.read_average(), vto.render_average(vto.make_scene(d), 9)).all()
 
 
+def test_pools_follow_the_frame_size():
+    """The wavefront pools are sized by paths per batch PLUS a queue slack that grows with the number of warps appending to the shade
+    queues (one partly filled chunk per warp and queue): a small frame with many passes, then a frame with 40x the pixels and the same
+    number of paths per batch, must re-size the slack (wf_slack_alloc) instead of running past the queues. Checked against the
+    megakernel, which has no queues, bit for bit; and back down again."""
+    ctx = vt.Context(0)
+    try:
+        vol = util.scene_fall_volume()
+        for W, H, passes in ((64, 64, 160), (704, 640, 2), (64, 64, 3), (1280, 704, 1)):
+            d = util.make_frame(vol, W, H, bounces=3, theta=120, phi=30)
+            util.upload(ctx, d)
+            imgs = []
+            for variant in (2, 0):
+                ctx.set_kernel_variant(variant)
+                ctx.reset_accumulation()
+                ctx.render(0, passes)
+                imgs.append(ctx.read_average())
+            ctx.set_kernel_variant(2)
+            assert util.same_bits(imgs[0], imgs[1]).all(), (W, H, passes)
+    finally:
+        ctx.close()
+
+
 def test_errors_are_reported_not_papered_over():
     ctx = vt.Context(0)
     try:

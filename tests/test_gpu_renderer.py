@@ -103,10 +103,10 @@ def test_renderer_c2_flow_env_thin_lens_autofocus(renderer, tmp_path):
     exr = str(tmp_path / "o.exr")
     r.saveImage(exr)
     assert util.same_bits(vt.host.load_image(exr), got[::-1, :, :3]).all()
-    pfm_env = str(tmp_path / "env.pfm")
+    pfm_env = str(tmp_path / "env2.pfm")                       # a new name: the renderer keeps an image it has already loaded (renderer.cpp:953)
     vt.host.write_pfm(pfm_env, np.nan_to_num(got[::-1, :, :3], nan=0.0))
     r.setRenderSettings(backgroundImage=pfm_env); r.resetRender(); r.renderPasses(2); from_pfm = r.context().read_average()
-    exr_env = str(tmp_path / "env.exr")
+    exr_env = str(tmp_path / "env2.exr")
     vt.host.write_exr(exr_env, np.nan_to_num(got[::-1, :, :3], nan=0.0))
     r.setRenderSettings(backgroundImage=exr_env); r.resetRender(); r.renderPasses(2)
     assert util.same_bits(r.context().read_average(), from_pfm).all()             # same pixels in, same frame out
