@@ -44,7 +44,7 @@ namespace vt {
 
 constexpr int kWfQueues = 5;          // 0 = finish, 1..3 = material type 0..2, 4 = other material types
 #ifndef VT_WF_LIVE_MIN
-#define VT_WF_LIVE_MIN 20
+#define VT_WF_LIVE_MIN 26
 #endif
 #ifndef VT_WF_SHADE_THREADS
 #define VT_WF_SHADE_THREADS 128      // threads per wf_shade CTA (64 / 128 / 256 measured in round 1: 84.2 / 84.2 / 84.6 ms per step)
@@ -55,7 +55,8 @@ constexpr int kWfQueues = 5;          // 0 = finish, 1..3 = material type 0..2, 
 // wf_trace steps its rays in chunks of kWfStepChunk DDA iterations and keeps stepping, chunk after chunk, while at least
 // kWfLiveMin lanes still run a ray; only then does it pay for a retire + refill round (about as many instructions as a
 // chunk). Round 1 retired and refilled after every 16-iteration chunk: half the lanes had finished by then (rays average
-// 17 iterations on C2) and 21 of 32 lanes did work.
+// 17 iterations on C2) and 21 of 32 lanes did work. Re-tuned once the primary rays had left this kernel (they were its longest rays):
+// 16 / 20 / 24 / 26 / 28 / 30 lanes -> 65.0 / 62.6 / 61.3 / 60.7 / 60.8 / 60.9 ms per C2 step; C3 trace 68.2 -> 63.1 ms at 26.
 constexpr int kWfLiveMin = VT_WF_LIVE_MIN;
 #ifndef VT_WF_STEP_CHUNK
 #define VT_WF_STEP_CHUNK 16
@@ -66,7 +67,7 @@ constexpr int kWfStepChunk = VT_WF_STEP_CHUNK;
 #endif
 constexpr int kWfStepChunkSkip = VT_WF_STEP_CHUNK_SKIP;   // chunk of the kernel instance with the empty-space skip (one skip attempt per chunk)
 #ifndef VT_WF_GRAB
-#define VT_WF_GRAB 128
+#define VT_WF_GRAB 256
 #endif
 #ifndef VT_WF_SKIP_MIN_LANES
 #define VT_WF_SKIP_MIN_LANES 16
@@ -388,7 +389,7 @@ wf_generate_kernel(const Volume V, const Frame F, const RenderLaunch L, const Wf
 
 // ---------------------------------------------------------------------------------------------------------
 // wf_trace: the loop of dda.h:38-57 for the ray records of one generation, then the routing of the finished path.
-// Persistent warps; a warp reserves kWfGrab rays per atomic (a static round-robin deal of the blocks was 20 % slower: every
+// Persistent warps; a warp reserves up to kWfGrab rays per atomic (a static round-robin deal of the blocks was 20 % slower: every
 // launch then waits for its unluckiest warp) and its lanes refill from that range whenever fewer than kWfLiveMin of them
 // still run a ray. Ray index w in [0, 2n): w < n = shadow ray of slot w, else bounce / primary ray of slot w - n.
 // Finished bounce / primary rays are not routed by the few lanes that happen to retire in a round: they park (slot, hit
@@ -416,6 +417,9 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S,
     __syncwarp();
     const unsigned int n = cnt->tq;                                   // slots of this generation
     const unsigned int w_total = 2u * n;
+    // rays per hand-out: kWfGrab when the launch is large (fewer same-address atomics), less when it is small, so that every warp of
+    // the grid still gets about four ranges (a 1-pass frame has 0.5 M rays for 7 104 warps)
+    const unsigned int grab = max(32u, min((unsigned)kWfGrab, (w_total / (gridDim.x * (kWfTraceThreads / 32) * 4u)) & ~31u));
     unsigned int* __restrict__ vis = S.vis;
     Tally<COUNT> tl; tl.clear();
 
@@ -463,10 +467,10 @@ wf_trace_kernel(const Volume V, const Frame F, const WfState S,
         if (!exhausted && need != 0u) {
             if (range_next >= range_end) {
                 unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&cnt->work, (unsigned)kWfGrab);
+                if (lane == 0) base = atomicAdd(&cnt->work, grab);
                 base = __shfl_sync(full, base, 0);
                 range_next = base;
-                range_end = min(base + (unsigned)kWfGrab, w_total);
+                range_end = min(base + grab, w_total);
                 if (base >= w_total) { exhausted = true; range_end = range_next = 0; }
             }
             if (!have) {
