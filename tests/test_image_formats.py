@@ -191,6 +191,11 @@ def test_bad_files_are_refused(tmp_path):
     open(p, "wb").write(b"\x89PNG\r\n\x1a\n" + b"\0" * 40)
     with pytest.raises(IOError):
         host.load_image(p)
+    box = struct.pack("<iiii", 0, 0, 65535, 65535)                             # a 4 Gi-pixel data window in a 200-byte file
+    open(p, "wb").write(struct.pack("<II", 20000630, 2) + b"channels\0chlist\0" + struct.pack("<i", 19) + b"R\0" + struct.pack("<iBBBBii", 2, 0, 0, 0, 0, 1, 1) + b"\0"
+                        + b"compression\0compression\0" + struct.pack("<i", 1) + b"\0" + b"dataWindow\0box2i\0" + struct.pack("<i", 16) + box + b"\0")
+    with pytest.raises(IOError):
+        host.load_image(p)
     open(p, "wb").write(struct.pack("<II", 20000630, 2 | 0x200))               # tiled
     with pytest.raises(IOError):
         host.load_image(p)

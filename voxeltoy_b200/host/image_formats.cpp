@@ -136,7 +136,7 @@ bool readEXR(const std::string& path, unsigned int& outWidth, unsigned int& outH
     if (channels.empty() || compression < 0 || dw[2] < dw[0] || dw[3] < dw[1]) return fail("incomplete header");
     if (compression > 3) return fail("only NONE, RLE, ZIPS and ZIP compression are supported (not PIZ / PXR24 / B44 / DWA)");
     const int64_t W = (int64_t)dw[2] - dw[0] + 1, H = (int64_t)dw[3] - dw[1] + 1;
-    if (W <= 0 || H <= 0 || W > 65536 || H > 65536) return fail("unreasonable data window");
+    if (W <= 0 || H <= 0 || W > 65536 || H > 65536 || W * H > ((int64_t)1 << 28)) return fail("unreasonable data window");
     size_t line_bytes = 0;
     std::vector<size_t> ch_off(channels.size());
     for (size_t i = 0; i < channels.size(); ++i) {
@@ -307,7 +307,7 @@ bool readPNG(const std::string& path, unsigned int& outWidth, unsigned int& outH
         else if (!memcmp(type, "IEND", 4)) end = true;
         at += 12 + (size_t)len;
     }
-    if (W == 0 || H == 0 || W > 65536 || H > 65536) return fail("bad image size");
+    if (W == 0 || H == 0 || W > 65536 || H > 65536 || (uint64_t)W * H > ((uint64_t)1 << 28)) return fail("bad image size");
     if (interlace != 0) return fail("interlaced PNG files are not supported");
     int comps;
     switch (ctype) { case 0: comps = 1; break; case 2: comps = 3; break; case 3: comps = 1; break; case 4: comps = 2; break; case 6: comps = 4; break; default: return fail("bad colour type"); }
