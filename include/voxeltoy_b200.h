@@ -213,6 +213,11 @@ int vt_measure_l2_bandwidth(vt_ctx* ctx, size_t bytes, int reps, float* gb_per_s
 int vt_debug_advance(vt_ctx* ctx, const float* d, const float* e, const float* tau, const int32_t* nmax, size_t n,
                      float* d_out, int32_t* k_out, int literal);
 
+/* test hook: the 3-instruction division by a compile-time constant (csrc/vt_math.cuh, gdiv_by) against div.rn for ALL 2^32
+ * numerators on the device; which = 0: PI, 1: 2 PI (the constants of shaders/shared/constants.h:1-3 the path divides by).
+ * mismatches = how many numerators give different bits (NaN == NaN), first_bad = the smallest such bit pattern. */
+int vt_debug_div_const(vt_ctx* ctx, int which, uint64_t* mismatches, uint32_t* first_bad);
+
 /* ---- render groups: one frame sharded over several GPUs (new-build surface; the reference renders on a single GL context,
  * renderer/renderer.cpp:556-645). Paths are independent and the scene is replicated (every context of the group receives
  * the same uploads through the vt_* calls above), so rendering needs no collective; the group owns the partition

@@ -53,6 +53,14 @@ def test_many_passes_continue_the_running_average(vt_ctx):
     assert util.same_bits(vt_ctx.read_average(), vto.render_average(vto.make_scene(d), 9)).all()
 
 
+def test_division_by_constants_is_exact(vt_ctx):
+    """x / PI and x / (2 PI) are computed as RN(x * rc) corrected by one exact residual (csrc/vt_math.cuh, gdiv_by): checked against
+    div.rn for EVERY binary32 numerator -- zeros, denormals, infinities and NaNs included -- on the device."""
+    for which in (0, 1):
+        bad, first = vt_ctx.debug_div_const(which)
+        assert bad == 0, "constant %d: %d numerators differ, first 0x%08x" % (which, bad, first)
+
+
 def test_pools_follow_the_frame_size():
     """The wavefront pools are sized by paths per batch PLUS a queue slack that grows with the number of warps appending to the shade
     queues (one partly filled chunk per warp and queue): a small frame with many passes, then a frame with 40x the pixels and the same

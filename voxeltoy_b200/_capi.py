@@ -79,6 +79,7 @@ SIGNATURES = {
     "vt_set_empty_skip": (C.c_int, [P, C.c_int]),
     "vt_measure_l2_bandwidth": (C.c_int, [P, C.c_size_t, C.c_int, f32p]),
     "vt_debug_advance": (C.c_int, [P, f32p, f32p, f32p, i32p, C.c_size_t, f32p, i32p, C.c_int]),
+    "vt_debug_div_const": (C.c_int, [P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "vt_counters_enable": (C.c_int, [P, C.c_int]),
     "vt_get_counters": (C.c_int, [P, C.POINTER(VtCounters)]),
     "vt_reset_counters": (C.c_int, [P]),
@@ -366,6 +367,12 @@ class Context:
         out = np.empty_like(d); k = np.empty_like(nmax)
         self._ck(self.lib.vt_debug_advance(self.h, _fp(d), _fp(e), _fp(tau), _ip(nmax), d.size, _fp(out), _ip(k), 1 if literal else 0))
         return out, k
+
+    def debug_div_const(self, which):
+        """(mismatches, first bad bit pattern) of gdiv_by vs div.rn over all 2^32 numerators; which = 0: PI, 1: 2 PI"""
+        m = C.c_uint64(); f = C.c_uint32()
+        self._ck(self.lib.vt_debug_div_const(self.h, int(which), C.byref(m), C.byref(f)))
+        return int(m.value), int(f.value)
 
     def measure_l2_bandwidth(self, nbytes=48 << 20, reps=20):
         g = C.c_float()

@@ -1193,6 +1193,25 @@ int vt_debug_advance(vt_ctx* c, const float* d, const float* e, const float* tau
     return VT_OK;
 }
 
+int vt_debug_div_const(vt_ctx* c, int which, uint64_t* mismatches, uint32_t* first_bad)
+{
+    if (!c || !mismatches || !first_bad || which < 0 || which > 1) return VT_ERR_INVALID;
+    VT_BIND(c);
+    unsigned long long* d_m = nullptr; unsigned int* d_f = nullptr;
+    VT_CUDA(c, cudaMalloc(&d_m, 8)); VT_CUDA(c, cudaMalloc(&d_f, 4));
+    VT_CUDA(c, cudaMemsetAsync(d_m, 0, 8, c->stream)); VT_CUDA(c, cudaMemsetAsync(d_f, 0xff, 4, c->stream));
+    vt_div_const_kernel<<<148 * 8, 256, 0, c->stream>>>(which, d_m, d_f);
+    c->launches += 1;
+    VT_CUDA(c, cudaGetLastError());
+    unsigned long long m = 0; unsigned int f = 0;
+    VT_CUDA(c, cudaMemcpyAsync(&m, d_m, 8, cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaMemcpyAsync(&f, d_f, 4, cudaMemcpyDeviceToHost, c->stream));
+    VT_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_m); cudaFree(d_f);
+    *mismatches = m; *first_bad = f;
+    return VT_OK;
+}
+
 int vt_debug_trace_rays(vt_ctx* c, const float* rays, size_t n, float* out)
 {
     if (!c || !rays || !out) return VT_ERR_INVALID;

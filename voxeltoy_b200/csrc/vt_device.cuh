@@ -543,7 +543,7 @@ VT_DEV f2 uv_from_vector(f3 v, float rot)                         // coordinates
 {
     const float theta = gacos(v.y);
     const float phi = gatan2(v.z, v.x) + VT_PI + rot;
-    return mk2(gmod(phi / VT_TWO_PI, 1.0f), theta / VT_PI);
+    return mk2(gmod(gdiv_two_pi(phi), 1.0f), gdiv_pi(theta));
 }
 VT_DEV f3 direction_from_uv(f2 uv, float rot)                     // coordinates.h:111-116 + :85-89
 {
@@ -568,7 +568,7 @@ VT_DEV f4 cosine_hemisphere(float ux, float uy)                   // sampling.h:
 {
     const f2 p = sample_disk(ux, uy);
     const float y = sqrtf(gmax(0.0f, 1.0f - p.x * p.x - p.y * p.y));
-    return mk4(p.x, y, p.y, y / VT_PI);
+    return mk4(p.x, y, p.y, gdiv_pi(y));
 }
 VT_DEV f4 uniform_hemisphere(float ux, float uy)                  // sampling.h:27-36
 {
@@ -811,7 +811,7 @@ VT_DEV f4 evaluate_material(const Frame& F, int off, f3 wo, f3 wi, Tally<COUNT>&
     VT_TALLY(H, 1);
     off += 1;
     switch (type) {
-    case 0: { const f3 a = mat_vec(F, off + 3); return mk4(a / VT_PI, wi.y / VT_PI); }               // matte.h:1-10, lambertian.h:23-29
+    case 0: { const f3 a = mat_vec(F, off + 3); return mk4(mk3(gdiv_pi(a.x), gdiv_pi(a.y), gdiv_pi(a.z)), gdiv_pi(wi.y)); }               // matte.h:1-10, lambertian.h:23-29
     case 1:                                                                                            // metal.h:1-17
     case 2: {                                                                                          // plastic.h:1-17 (reflectance 1)
         const f3 refl = (type == 1) ? mat_vec(F, off + 3) : mk3(1.0f);
@@ -831,7 +831,7 @@ VT_DEV f3 sample_material(const Frame& F, int off, f3 wo, int2& rng, f4& f_pdf, 
     if (type == 0) {                                              // matte.h:12-22, lambertian.h:10-19
         const f3 a = mat_vec(F, off + 3);
         const f4 l = cosine_hemisphere(u.x, u.y);
-        f_pdf = mk4(a / VT_PI, l.w);
+        f_pdf = mk4(mk3(gdiv_pi(a.x), gdiv_pi(a.y), gdiv_pi(a.z)), l.w);
         return xyz(l);
     }
     const f3 refl = (type == 1) ? mat_vec(F, off + 3) : mk3(1.0f);   // metal.h:19-36; plastic.h:19-28 (reflectance 1)

@@ -53,6 +53,25 @@ VT_DEV_HEAVY float gdiv(float a, float b)
     return a / b;
 }
 
+// Division by a COMPILE-TIME constant c (the shaders divide by PI and 2 PI about ten times per shaded hit): with rc = RN(1 / c),
+//   q0 = RN(a * rc),  r = a - c * q0 (exact, one FMA),  q = RN(q0 + r * rc)
+// is the correctly rounded quotient (Markstein; q0 is within an ulp of a / c and the residual is exact) -- 3 instructions instead of
+// the ~15 of the called IEEE sequence. The argument needs normal operands and results: zeros (sign!), infinities, NaN and anything
+// below 1e-30 take gdiv. Not taken on trust: vt_debug_div_const compares it with div.rn for ALL 2^32 numerators on the device
+// (tests/test_gpu_edges.py::test_division_by_constants_is_exact), for every constant used below.
+VT_DEV float gdiv_by(float a, const float c, const float rc)
+{
+    const float aa = __int_as_float(__float_as_int(a) & 0x7fffffff);
+    if (!(aa >= 1.0e-30f && aa < __int_as_float(0x7f800000))) return gdiv(a, c);
+    const float q0 = a * rc;
+    const float r = fmaf(-c, q0, a);          // an explicit fma: -fmad=false only forbids CONTRACTING a * b + c
+    return fmaf(r, rc, q0);
+}
+#define VT_PI_F        3.14159265359f
+#define VT_TWO_PI_F    6.28318530718f
+VT_DEV float gdiv_pi(float a) { return gdiv_by(a, VT_PI_F, 1.0f / VT_PI_F); }
+VT_DEV float gdiv_two_pi(float a) { return gdiv_by(a, VT_TWO_PI_F, 1.0f / VT_TWO_PI_F); }
+
 VT_DEV f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
 VT_DEV f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
 VT_DEV f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
