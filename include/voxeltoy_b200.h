@@ -214,7 +214,8 @@ int vt_debug_advance(vt_ctx* ctx, const float* d, const float* e, const float* t
                      float* d_out, int32_t* k_out, int literal);
 
 /* test hook: the 3-instruction division by a compile-time constant (csrc/vt_math.cuh, gdiv_by) against div.rn for ALL 2^32
- * numerators on the device; which = 0: PI, 1: 2 PI (the constants of shaders/shared/constants.h:1-3 the path divides by).
+ * numerators on the device; which = 0: PI, 1: 2 PI (the constants of shaders/shared/constants.h:1-3 the path divides by);
+ * which = 2: the direction clamp of dda.h:29 as one select (gclamp_dir) against the literal mix / step, for all 2^32 inputs.
  * mismatches = how many numerators give different bits (NaN == NaN), first_bad = the smallest such bit pattern. */
 int vt_debug_div_const(vt_ctx* ctx, int which, uint64_t* mismatches, uint32_t* first_bad);
 

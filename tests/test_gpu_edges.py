@@ -56,7 +56,7 @@ def test_many_passes_continue_the_running_average(vt_ctx):
 def test_division_by_constants_is_exact(vt_ctx):
     """x / PI and x / (2 PI) are computed as RN(x * rc) corrected by one exact residual (csrc/vt_math.cuh, gdiv_by): checked against
     div.rn for EVERY binary32 numerator -- zeros, denormals, infinities and NaNs included -- on the device."""
-    for which in (0, 1):
+    for which in (0, 1, 2):                                          # / PI, / 2 PI, and the direction clamp of dda.h:29 as one select
         bad, first = vt_ctx.debug_div_const(which)
         assert bad == 0, "constant %d: %d numerators differ, first 0x%08x" % (which, bad, first)
 

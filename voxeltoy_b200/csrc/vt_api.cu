@@ -1195,7 +1195,7 @@ int vt_debug_advance(vt_ctx* c, const float* d, const float* e, const float* tau
 
 int vt_debug_div_const(vt_ctx* c, int which, uint64_t* mismatches, uint32_t* first_bad)
 {
-    if (!c || !mismatches || !first_bad || which < 0 || which > 1) return VT_ERR_INVALID;
+    if (!c || !mismatches || !first_bad || which < 0 || which > 2) return VT_ERR_INVALID;
     VT_BIND(c);
     unsigned long long* d_m = nullptr; unsigned int* d_f = nullptr;
     VT_CUDA(c, cudaMalloc(&d_m, 8)); VT_CUDA(c, cudaMalloc(&d_f, 4));

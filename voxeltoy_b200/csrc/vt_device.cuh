@@ -243,9 +243,7 @@ VT_DEV int dda_begin(const Volume& V, f3 o, f3 d, Dda& s, Tally<COUNT>& tl)
     const f3 vp = gfloor(vo);                                     // :22
     if (out_of_grid(vp, V.resf)) return DDA_NOHIT;                // :24-25
     // :29  mix(d, 1e-5, step(abs(d), 1e-5))
-    d = mk3(gmix(d.x, 1e-5f, gstep(gabs(d.x), 1e-5f)),
-            gmix(d.y, 1e-5f, gstep(gabs(d.y), 1e-5f)),
-            gmix(d.z, 1e-5f, gstep(gabs(d.z), 1e-5f)));
+    d = mk3(gclamp_dir(d.x), gclamp_dir(d.y), gclamp_dir(d.z));
     const f3 inc = mk3(1.0f) / d;                                 // :31
     const f3 sg = gsign(d);                                       // :32
     const f3 dis = (((vp - vo) + 0.5f) + sg * 0.5f) * inc;        // :34

@@ -455,14 +455,14 @@ VT_GLOBAL void vt_advance_kernel(const float* __restrict__ d, const float* __res
     d_out[i] = x; k_out[i] = k;
 }
 
-// test hook: gdiv_by against div.rn for every binary32 numerator (which = 0: PI, 1: 2 PI)
+// test hook: gdiv_by against div.rn (which = 0: PI, 1: 2 PI) and gclamp_dir against the literal mix / step (which = 2), for every binary32 input
 VT_GLOBAL void vt_div_const_kernel(int which, unsigned long long* __restrict__ mismatches, unsigned int* __restrict__ first_bad)
 {
     unsigned long long bad = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += (unsigned long long)gridDim.x * blockDim.x) {
         const float a = __int_as_float((int)(unsigned int)i);
-        const float want = which == 0 ? __fdiv_rn(a, VT_PI_F) : __fdiv_rn(a, VT_TWO_PI_F);
-        const float got = which == 0 ? gdiv_pi(a) : gdiv_two_pi(a);
+        const float want = which == 0 ? __fdiv_rn(a, VT_PI_F) : (which == 1 ? __fdiv_rn(a, VT_TWO_PI_F) : gmix(a, 1e-5f, gstep(gabs(a), 1e-5f)));
+        const float got = which == 0 ? gdiv_pi(a) : (which == 1 ? gdiv_two_pi(a) : gclamp_dir(a));
         const bool same = (__float_as_int(want) == __float_as_int(got)) || (want != want && got != got);
         if (!same) { if (bad == 0) atomicMin(first_bad, (unsigned int)i); ++bad; }
     }

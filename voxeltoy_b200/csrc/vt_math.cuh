@@ -92,6 +92,10 @@ VT_DEV float gmix(float x, float y, float a) { return x * (1.0f - a) + y * a; }
 VT_DEV float gmod(float x, float y) { return x - y * floorf(x / y); }
 VT_DEV float gclamp(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
 VT_DEV int f2i(float f) { return __float2int_rz(f); }
+// dda.h:29  mix(d, 1e-5, step(abs(d), 1e-5)) = d * (1 - a) + 1e-5 * a with a = (1e-5 < |d|) ? 0 : 1. For |d| > 1e-5 that is d * 1 + 0 = d
+// (d is not zero there, so adding +0 changes nothing), for |d| <= 1e-5 it is +-0 + 1e-5 = 1e-5, and a NaN stays a NaN: one compare
+// and one select instead of seven instructions per component. Same bits for every binary32 d (vt_debug_div_const, which = 2).
+VT_DEV float gclamp_dir(float d) { return !(gabs(d) <= 1e-5f) ? d : 1e-5f; }
 
 VT_DEV f3 gabs(f3 a) { return mk3(gabs(a.x), gabs(a.y), gabs(a.z)); }
 VT_DEV f3 gsign(f3 a) { return mk3(gsign(a.x), gsign(a.y), gsign(a.z)); }
