@@ -172,6 +172,25 @@ def test_png_writer_is_read_back(tmp_path):
         assert theirs is not None and np.array_equal(theirs[..., [2, 1, 0, 3]], rgba)
 
 
+def test_hdr_writer_is_read_back(tmp_path):
+    """Radiance RGBE keeps 8 bits of the largest component and a shared exponent: the round trip is exact for what the format holds,
+    within 1 / 128 of the largest component otherwise; OpenCV's reader agrees with ours."""
+    img = _image(h=21, w=33, seed=6)
+    img[1, 1, 0] = 4.0
+    p = str(tmp_path / "w.hdr")
+    host.write_hdr(p, img)
+    back = host.load_image(p)
+    m = img.max(axis=2, keepdims=True)
+    assert back.shape == img.shape and (np.abs(back - img) <= m / 128.0 + 1e-30).all()
+    host.write_hdr(p, back)                                   # what RGBE can hold survives unchanged
+    assert np.array_equal(host.load_image(p), back)
+    cv2 = _cv2()
+    if cv2 is not None:
+        theirs = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+        if theirs is not None:
+            assert np.allclose(theirs[..., ::-1], back, rtol=1e-6, atol=0)
+
+
 def test_reference_screenshot_if_present():
     """The reference's own PNG resources (this container only; the file does not travel)."""
     path = "/root/reference/resources/screenshot01.png"

@@ -72,6 +72,7 @@ _SIG = {
     "vth_widget_update_pending": (C.c_int, [P]), "vth_widget_paints": (C.c_ulong, [P]),
     "vth_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint, C.c_uint]),
     "vth_write_exr": (C.c_int, [C.c_char_p, f32p, C.c_uint, C.c_uint, C.c_int]),
+    "vth_write_hdr": (C.c_int, [C.c_char_p, f32p, C.c_uint, C.c_uint, C.c_int]),
     "vth_load_image_dims": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "vth_load_image": (C.c_int, [C.c_char_p, f32p]),
 }
@@ -213,6 +214,14 @@ def write_exr(path, pixels):
     pixels = np.ascontiguousarray(pixels, np.float32)
     assert pixels.ndim == 3 and pixels.shape[2] in (3, 4)
     if lib().vth_write_exr(path.encode(), _fp(pixels), pixels.shape[1], pixels.shape[0], pixels.shape[2]) != 0:
+        raise IOError("cannot write " + path)
+
+
+def write_hdr(path, pixels):
+    """writeHDR (host/image.cpp): (h, w, 3 or 4) float32, rows top-down -> Radiance RGBE"""
+    pixels = np.ascontiguousarray(pixels, np.float32)
+    assert pixels.ndim == 3 and pixels.shape[2] in (3, 4)
+    if lib().vth_write_hdr(path.encode(), _fp(pixels), pixels.shape[1], pixels.shape[0], pixels.shape[2]) != 0:
         raise IOError("cannot write " + path)
 
 

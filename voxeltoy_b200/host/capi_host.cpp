@@ -217,6 +217,7 @@ void vth_cdf_free(void* hd) { delete static_cast<CdfResult*>(hd); }
 int vth_write_pfm(const char* path, const float* rgb, unsigned int w, unsigned int h) { return writePFM(path, rgb, w, h) ? 0 : -1; }
 int vth_write_png(const char* path, const unsigned char* rgba8, unsigned int w, unsigned int h) { return writePNG(path, rgba8, w, h) ? 0 : -1; }
 int vth_write_exr(const char* path, const float* pixels, unsigned int w, unsigned int h, int channels) { return writeEXR(path, pixels, w, h, channels) ? 0 : -1; }
+int vth_write_hdr(const char* path, const float* pixels, unsigned int w, unsigned int h, int stride) { return writeHDR(path, pixels, w, h, stride) ? 0 : -1; }
 int vth_load_image_dims(const char* path, unsigned int* w, unsigned int* h)
 {
     std::vector<float> px;

@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <zlib.h>
+
 #define MAX_CDF_SIZE 512          // image.cpp:14
 
 // ---- file I/O --------------------------------------------------------------------------------------------------------
@@ -128,6 +130,31 @@ static bool write_chunk(FILE* fp, const char type[4], const std::vector<unsigned
         && fwrite(&tail[0], 1, 4, fp) == 4;
 }
 
+// Radiance .hdr (RGBE, flat scanlines -- every reader accepts them), rows top-down; `stride` floats per pixel (3 or 4), RGB first
+bool writeHDR(const std::string& path, const float* pixels, unsigned int w, unsigned int h, int stride)
+{
+    if (!pixels || w == 0 || h == 0 || stride < 3) return false;
+    FILE* fp = fopen(path.c_str(), "wb");
+    if (!fp) return false;
+    fprintf(fp, "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %u +X %u\n", h, w);
+    std::vector<unsigned char> line((size_t)w * 4);
+    for (unsigned int y = 0; y < h; ++y) {
+        for (unsigned int x = 0; x < w; ++x) {
+            const float* p = pixels + ((size_t)y * w + x) * stride;
+            float r = p[0], g = p[1], b = p[2];
+            if (!(r > 0.0f)) r = 0.0f; if (!(g > 0.0f)) g = 0.0f; if (!(b > 0.0f)) b = 0.0f;         // RGBE holds no negatives and no NaN
+            const float m = std::max(r, std::max(g, b));
+            unsigned char* o = &line[(size_t)x * 4];
+            if (m < 1e-32f || !(m < 3.0e38f)) { o[0] = o[1] = o[2] = o[3] = 0; if (!(m < 3.0e38f)) { o[0] = o[1] = o[2] = 255; o[3] = 255; } continue; }
+            int e; const float f = std::frexp(m, &e) * 256.0f / m;
+            o[0] = (unsigned char)(r * f); o[1] = (unsigned char)(g * f); o[2] = (unsigned char)(b * f); o[3] = (unsigned char)(e + 128);
+        }
+        fwrite(&line[0], 1, line.size(), fp);
+    }
+    const bool ok = ferror(fp) == 0;
+    return (fclose(fp) == 0) && ok;
+}
+
 bool writePNG(const std::string& path, const unsigned char* rgba8, unsigned int w, unsigned int h)
 {
     if (!rgba8 || w == 0 || h == 0) return false;
@@ -141,18 +168,10 @@ bool writePNG(const std::string& path, const unsigned char* rgba8, unsigned int 
     const size_t stride = (size_t)w * 4 + 1, rawSize = stride * h;                                   // filter byte 0 (None) per scanline
     std::vector<unsigned char> raw(rawSize);
     for (unsigned int y = 0; y < h; ++y) { raw[y * stride] = 0; memcpy(&raw[y * stride + 1], rgba8 + (size_t)y * w * 4, (size_t)w * 4); }
-    uint32_t a = 1, b = 0;                                                                           // Adler-32, deferred modulo (5552 bytes)
-    for (size_t i = 0; i < rawSize;) { const size_t n = std::min<size_t>(5552, rawSize - i); for (size_t k = 0; k < n; ++k) { a += raw[i + k]; b += a; } a %= 65521u; b %= 65521u; i += n; }
-    std::vector<unsigned char> z; z.reserve(rawSize + rawSize / 65535 * 5 + 16);
-    z.push_back(0x78); z.push_back(0x01);                                                            // zlib header: deflate, 32 K window, no preset
-    for (size_t i = 0; i < rawSize;) {
-        const size_t n = std::min<size_t>(65535, rawSize - i);
-        z.push_back(i + n == rawSize ? 1 : 0);                                                       // BFINAL, BTYPE = 00 (stored)
-        z.push_back(n & 0xFF); z.push_back((n >> 8) & 0xFF); z.push_back(~n & 0xFF); z.push_back((~n >> 8) & 0xFF);
-        z.insert(z.end(), raw.begin() + i, raw.begin() + i + n);
-        i += n;
-    }
-    put_be32(z, (b << 16) | a);
+    uLongf zn = compressBound((uLong)rawSize);                                                       // zlib stream: deflate level 6
+    std::vector<unsigned char> z(zn);
+    ok = ok && compress2(&z[0], &zn, &raw[0], (uLong)rawSize, 6) == Z_OK;
+    z.resize(ok ? zn : 0);
     ok = ok && write_chunk(fp, "IDAT", z) && write_chunk(fp, "IEND", std::vector<unsigned char>());
     return (fclose(fp) == 0) && ok;
 }

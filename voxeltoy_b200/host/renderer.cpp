@@ -314,10 +314,11 @@ void Renderer::saveImage(const std::string& file)                               
     }
     std::vector<float> pixels((size_t)xres * yres * 4);
     if (!readAverage(&pixels[0])) return;
-    if (ext == ".exr") {                                                       // float RGBA, rows top-down: the flip of :1131-1136 on the host
+    if (ext == ".exr" || ext == ".hdr") {                                      // float formats, rows top-down: the flip of :1131-1136 on the host
         std::vector<float> top((size_t)xres * yres * 4);
         for (int y = 0; y < yres; ++y) memcpy(&top[(size_t)y * xres * 4], &pixels[(size_t)(yres - 1 - y) * xres * 4], (size_t)xres * 4 * sizeof(float));
-        if (!writeEXR(file, &top[0], xres, yres, 4)) log("could not write " + file);
+        const bool ok = ext == ".exr" ? writeEXR(file, &top[0], xres, yres, 4) : writeHDR(file, &top[0], xres, yres, 4);
+        if (!ok) log("could not write " + file);
         return;
     }
     FILE* fp = fopen(file.c_str(), "wb");

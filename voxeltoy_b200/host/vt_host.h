@@ -263,7 +263,8 @@ bool calculateCDF(const float* rgbPixels, unsigned int imageWidth, unsigned int 
                   std::vector<float>& cdfUData, unsigned int& cdfUDataWidth, unsigned int& cdfUDataHeight,
                   std::vector<float>& cdfVData, float& environmentTextureIntegral);
 bool writePFM(const std::string& path, const float* rgb, unsigned int w, unsigned int h);
-bool writePNG(const std::string& path, const unsigned char* rgba8, unsigned int w, unsigned int h);   // rows top-down, stored deflate
+bool writePNG(const std::string& path, const unsigned char* rgba8, unsigned int w, unsigned int h);   // rows top-down, zlib deflate
+bool writeHDR(const std::string& path, const float* pixels, unsigned int w, unsigned int h, int stride);   // Radiance RGBE, rows top-down
 // image_formats.cpp: OpenEXR (scanline; NONE / RLE / ZIPS / ZIP; HALF / FLOAT / UINT) and PNG readers, OpenEXR writer (FLOAT, ZIP); rows top-down
 bool readEXR(const std::string& path, unsigned int& outWidth, unsigned int& outHeight, std::vector<float>& rgb, std::string* why = nullptr);
 bool readPNG(const std::string& path, unsigned int& outWidth, unsigned int& outHeight, std::vector<float>& rgb, std::string* why = nullptr);
